@@ -1,0 +1,77 @@
+"""Build recipe for libeogs_raster.so (sm_100a only, in-tree).
+
+`python -m eogs2_b200.build` compiles every csrc/*.cu with nvcc for
+`-gencode arch=compute_100a,code=sm_100a -lineinfo` and links one shared library,
+`eogs2_b200/libeogs_raster.so`, whose only exports are the extern "C" entry points
+declared in include/eogs_raster.h.  nvcc cross-compiles without a GPU.  The library
+does not link against torch: the Python mirror talks to it through ctypes.
+
+No fast-math: key/range parity with the reference depends on IEEE div/sqrt and the
+accurate expf (the reference build uses nvcc defaults, DGR/setup.py:32-38).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+BUILD = PKG_DIR / "csrc" / "build"
+LIB = PKG_DIR / "libeogs_raster.so"
+SOURCES = ["cabi.cu", "preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+                     "-Xptxas", "-v", "--expt-relaxed-constexpr", "-Wno-deprecated-declarations"]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (needed to build libeogs_raster.so for sm_100a)")
+
+
+def _deps_mtime() -> float:
+    hdrs = list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "eogs_raster.h", Path(__file__)]
+    return max(p.stat().st_mtime for p in hdrs)
+
+
+def _compile(src: str, nvcc: str, force: bool, log: list) -> Path:
+    s = CSRC / src
+    o = BUILD / (src.replace(".cu", ".o"))
+    if not force and o.exists() and o.stat().st_mtime > max(s.stat().st_mtime, _deps_mtime()):
+        return o
+    cmd = [nvcc, *NVCC_FLAGS, "-c", str(s), "-o", str(o)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    log.append((src, r.stderr))
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+    return o
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    nvcc = nvcc_path()
+    BUILD.mkdir(parents=True, exist_ok=True)
+    log: list = []
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(lambda s: _compile(s, nvcc, force, log), SOURCES))
+    newest = max(o.stat().st_mtime for o in objs)
+    if force or not LIB.exists() or LIB.stat().st_mtime < newest:
+        cmd = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB), *map(str, objs)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    if verbose:
+        for src, err in log:
+            print(f"--- {src}\n{err}")
+    (BUILD / "ptxas.log").write_text("\n".join(f"--- {s}\n{e}" for s, e in log) if log else "")
+    return LIB
+
+
+if __name__ == "__main__":
+    lib = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(lib)

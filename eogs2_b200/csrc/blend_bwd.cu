@@ -1,0 +1,215 @@
+// Backward blend: one 256-thread block per tile, one thread per pixel, back-to-front replay of
+// the tile's list.  Replaces renderCUDA<5> backward (DGR/cuda_rasterizer/backward.cu:458-643).
+//
+// The reference issues 12 atomicAdd(float) to global memory per contributing (pixel, Gaussian)
+// pair (backward.cu:598,608,631-640).  Here the 6+C per-pair terms are first summed over the
+// 32 pixels of a warp with a transposing butterfly (fold): at each of the 5 shuffle levels a
+// lane keeps half of its values and sends the other half, so N values cost N/2 + N/4 + ... + 1
+// = 13 shuffles for N = 11 instead of 5*N = 55, and the result ends up spread over the lanes —
+// one value per even lane — which then issue ONE red.global.add.f32 warp instruction into the
+// Gaussian's contiguous 64-byte gradient record.  Warps in which no pixel is touched by the
+// Gaussian (ballot == 0) skip everything after the alpha test.
+//
+// Other differences from the reference kernel
+//   - the replay starts at the tile's max(n_contrib) instead of the end of the list, so list
+//     entries nobody blended are never fetched (the reference stages and skips them);
+//   - the per-channel accum_rec / last_color recurrences (backward.cu:584-596) are collapsed
+//     into one scalar recurrence on the dot product with dL_dpixel (same linear map);
+//   - dL_dinvdepth per Gaussian is not accumulated: the reference computes it and drops it
+//     (backward.cu:305-307 commented out; it never reaches a returned gradient);
+//   - packed 48-byte records gathered with cp.async, double-buffered (see blend_fwd.cu).
+//
+// Bound: FP32 issue + shuffle + L2 reduction throughput.  Algorithmic HBM bytes: 52 B gathered +
+// <= 8 warps x 44 B reduced per instance, 4*(C+1) + 8 B per pixel in.
+#include "common.cuh"
+
+namespace eogs {
+
+constexpr int BWD_THREADS = TILE_PIXELS;
+
+// Transposing butterfly level: N live values -> ceil(N/2), partner = lane ^ (1 << BIT).
+template <int N, int BIT>
+__device__ __forceinline__ void fold(float* v, uint32_t lane) {
+    constexpr int HALF = (N + 1) / 2;
+    const bool upper = (lane >> BIT) & 1u;
+#pragma unroll
+    for (int k = 0; k < HALF; k++) {
+        const float hi = (k + HALF < N) ? v[k + HALF] : 0.f;
+        const float keep = upper ? hi : v[k];
+        const float send = upper ? v[k] : hi;
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << BIT);
+    }
+}
+
+// After fold<N,4>, <N1,3>, <N2,2>, <N3,1> and a final xor-1 add, lane L holds the warp total of
+// value slot(L) in v[0]; returns -1 for lanes that hold nothing.
+template <int N>
+__device__ __forceinline__ int fold_slot(uint32_t lane) {
+    constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2;
+    static_assert(N4 == 1, "fold supports up to 16 values");
+    const int b1 = (lane >> 1) & 1, b2 = (lane >> 2) & 1, b3 = (lane >> 3) & 1, b4 = (lane >> 4) & 1;
+    int pos = b1 * N4;
+    if (pos >= N3) return -1;
+    pos += b2 * N3;
+    if (pos >= N2) return -1;
+    pos += b3 * N2;
+    if (pos >= N1) return -1;
+    pos += b4 * N1;
+    if (pos >= N) return -1;
+    return (lane & 1u) ? -1 : pos;
+}
+
+template <int N>
+__device__ __forceinline__ void warp_transpose_reduce(float* v, uint32_t lane) {
+    constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2;
+    fold<N, 4>(v, lane);
+    fold<N1, 3>(v, lane);
+    fold<N2, 2>(v, lane);
+    fold<N3, 1>(v, lane);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int C>
+__global__ void __launch_bounds__(BWD_THREADS)
+blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                 const float4* __restrict__ splat, const float* __restrict__ bg, int W, int H,
+                 const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+                 const float* __restrict__ dL_dpix, const float* __restrict__ dL_dinvdepth,
+                 float* __restrict__ grad_rec)
+{
+    constexpr int NV = 6 + C;   // mean2D.xy, conic.xyw, opacity, colours
+    __shared__ float4 s_rec[2][REC_F4][BWD_THREADS];
+    __shared__ uint32_t s_id[2][BWD_THREADS];
+    __shared__ int s_nmax;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    uint32_t lx, ly;
+    tile_pixel(tid, lx, ly);
+    const uint32_t pix_x = blockIdx.x * TILE + lx, pix_y = blockIdx.y * TILE + ly;
+    const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
+    const size_t pix_id = (size_t)pix_y * W + pix_x;
+    const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+
+    const uint2 range = __ldg(ranges + blockIdx.y * gridDim.x + blockIdx.x);
+    const uint32_t* list = point_list + range.x;
+
+    const int last_contributor = inside ? (int)__ldg(n_contrib + pix_id) : 0;
+    if (tid == 0) s_nmax = 0;
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0 && wmax > 0) atomicMax(&s_nmax, wmax);
+    __syncthreads();
+    const int nmax = s_nmax;            // entries [nmax, n) were blended by no pixel of this tile
+    if (nmax == 0) return;
+    const int rounds = (nmax + BWD_THREADS - 1) / BWD_THREADS;
+
+    auto gather = [&](int stage, int batch) {
+        const int p = nmax - 1 - (batch * BWD_THREADS + (int)tid);   // back to front
+        if (p >= 0) {
+            const uint32_t id = __ldg(list + p);
+            s_id[stage][tid] = id;
+            const float4* src = splat + (size_t)id * REC_F4;
+#pragma unroll
+            for (int k = 0; k < REC_F4; k++) cp_async16(&s_rec[stage][k][tid], src + k);
+        }
+    };
+    gather(0, 0);
+    cp_async_commit();
+
+    const float T_final = inside ? __ldg(final_T + pix_id) : 0.f;
+    float T = T_final;
+    float g[C];
+    float bg_dot_g = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < C; ch++) {
+        g[ch] = inside ? __ldg(dL_dpix + (size_t)ch * H * W + pix_id) : 0.f;
+        bg_dot_g = fmaf(__ldg(bg + ch), g[ch], bg_dot_g);
+    }
+    const float g_inv = (inside && dL_dinvdepth) ? __ldg(dL_dinvdepth + pix_id) : 0.f;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    float last_alpha = 0.f, last_cg = 0.f, accum_rec = 0.f;
+    const int my_slot = fold_slot<NV>(lane);
+
+    for (int i = 0; i < rounds; i++) {
+        cp_async_wait<0>();
+        __syncthreads();
+        if (i + 1 < rounds) gather((i + 1) & 1, i + 1);
+        cp_async_commit();
+
+        const int stage = i & 1;
+        const int first = nmax - 1 - i * BWD_THREADS;          // list position of entry j = 0
+        const int cnt = min(BWD_THREADS, first + 1);
+        for (int j = 0; j < cnt; j++) {
+            // Entry at list position p is blended by this pixel iff p < n_contrib (backward.cu:556-558).
+            const bool active = (first - j) < last_contributor;
+            const float4 ra = s_rec[stage][0][j];
+            const float4 rb = s_rec[stage][1][j];
+            const float dx = __fsub_rn(ra.x, pixfx), dy = __fsub_rn(ra.y, pixfy);
+            const float quad = __fmaf_rn(dx, __fmul_rn(ra.z, dx), __fmul_rn(__fmul_rn(rb.x, dy), dy));
+            const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx), dy));
+            const float G = expf(power);
+            const float alpha = fminf(0.99f, __fmul_rn(rb.y, G));
+            const bool valid = active && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            if (!__any_sync(0xffffffffu, valid)) continue;
+
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; k++) v[k] = 0.f;
+            if (valid) {
+                const float4 rc = s_rec[stage][2][j];
+                const float col[5] = {rb.z, rb.w, rc.x, rc.y, rc.z};
+                const float inv_1ma = __fdividef(1.f, 1.f - alpha);
+                T *= inv_1ma;
+                const float w = alpha * T;
+                float cg = rc.w * g_inv;
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) {
+                    v[6 + ch] = w * g[ch];
+                    cg = fmaf(col[ch], g[ch], cg);
+                }
+                accum_rec = fmaf(last_alpha, last_cg, (1.f - last_alpha) * accum_rec);
+                last_cg = cg;
+                last_alpha = alpha;
+                float dL_dalpha = (cg - accum_rec) * T;
+                dL_dalpha = fmaf(-T_final * inv_1ma, bg_dot_g, dL_dalpha);
+
+                const float dL_dG = rb.y * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
+                const float dG_ddely = -gdy * rb.x - gdx * ra.w;
+                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                v[1] = dL_dG * dG_ddely * ddely_dy;
+                v[2] = -0.5f * gdx * dx * dL_dG;
+                v[3] = -0.5f * gdx * dy * dL_dG;
+                v[4] = -0.5f * gdy * dy * dL_dG;
+                v[5] = G * dL_dalpha;
+            }
+            warp_transpose_reduce<NV>(v, lane);
+            if (my_slot >= 0) atomicAdd(grad_rec + (size_t)s_id[stage][j] * GRAD_STRIDE + my_slot, v[0]);
+        }
+    }
+    cp_async_wait<0>();
+}
+
+int launch_blend_bwd(cudaStream_t s, int W, int H, int channels, const char* geom,
+                     const GeomLayout& GL, const uint32_t* point_list, const char* image,
+                     const ImageLayout& IL, const float* bg, const float* dL_dpix,
+                     const float* dL_dinvdepth, float* grad_rec)
+{
+    const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
+    auto run = [&](auto kernel) {
+        kernel<<<grid, BWD_THREADS, 0, s>>>(
+            reinterpret_cast<const uint2*>(image + IL.ranges), point_list,
+            reinterpret_cast<const float4*>(geom + GL.splat), bg, W, H,
+            reinterpret_cast<const float*>(image + IL.final_T),
+            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), dL_dpix, dL_dinvdepth, grad_rec);
+    };
+    if (channels == 5) run(blend_bwd_kernel<5>);
+    else if (channels == 3) run(blend_bwd_kernel<3>);
+    else { set_error("channels must be 3 or 5, got %d", channels); return -1; }
+    EOGS_LAUNCH_CHECK("blend_bwd_kernel");
+    return 0;
+}
+
+}  // namespace eogs

@@ -1,0 +1,237 @@
+// extern "C" surface of libeogs_raster.so (see include/eogs_raster.h for the contract and the
+// reference interfaces each entry point replaces).
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace eogs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+__global__ void fill_u8_kernel(uint8_t* p, int n, uint8_t v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// Rebuild the reference's per-Gaussian / per-instance views of our packed state.
+__global__ void export_geom_kernel(int P, const float4* __restrict__ splat, const float* __restrict__ depth,
+                                   const uint32_t* __restrict__ tiles, float* means2D, float* depths,
+                                   float* conic_opacity, uint32_t* tiles_touched) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float4 a = splat[(size_t)i * REC_F4], b = splat[(size_t)i * REC_F4 + 1];
+    if (means2D) { means2D[2 * (size_t)i] = a.x; means2D[2 * (size_t)i + 1] = a.y; }
+    if (depths) depths[i] = depth[i];
+    if (conic_opacity) {
+        conic_opacity[4 * (size_t)i] = a.z; conic_opacity[4 * (size_t)i + 1] = a.w;
+        conic_opacity[4 * (size_t)i + 2] = b.x; conic_opacity[4 * (size_t)i + 3] = b.y;
+    }
+    if (tiles_touched) tiles_touched[i] = tiles[i];
+}
+
+__global__ void export_keys_kernel(uint32_t num_tiles, const uint2* __restrict__ ranges,
+                                   const uint32_t* __restrict__ point_list,
+                                   const float* __restrict__ depth, uint64_t* keys) {
+    const uint32_t tile = blockIdx.x;
+    if (tile >= num_tiles) return;
+    const uint2 r = ranges[tile];
+    for (uint32_t j = r.x + threadIdx.x; j < r.y; j += blockDim.x)
+        keys[j] = ((uint64_t)tile << 32) | (uint64_t)__float_as_uint(depth[point_list[j]]);
+}
+
+static int check_common(int P, int W, int H, int channels) {
+    if (P < 0 || W <= 0 || H <= 0) { set_error("bad sizes P=%d W=%d H=%d", P, W, H); return -1; }
+    if (channels != 3 && channels != 5) { set_error("channels must be 3 or 5, got %d", channels); return -1; }
+    if ((W + TILE - 1) / TILE > 0xFFFF || (H + TILE - 1) / TILE > 0xFFFF) { set_error("image too large"); return -1; }
+    return 0;
+}
+
+}  // namespace eogs
+
+using namespace eogs;
+
+extern "C" {
+
+EOGS_API int eogs_abi_version(void) { return EOGS_ABI_VERSION; }
+EOGS_API const char* eogs_last_error(void) { return g_err; }
+
+EOGS_API size_t eogs_geom_bytes(int P) { return geom_layout(P).total; }
+EOGS_API size_t eogs_image_bytes(int W, int H) { return image_layout(W, H).total; }
+EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t I) { return binning_layout(W, H, I).total; }
+
+EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, int channels,
+                          const float* means3D, const float* scales, const float* rotations,
+                          const float* cov3D_precomp, const float* opacities, const float* colors,
+                          const float* viewmatrix, float scale_modifier, int antialiasing,
+                          int32_t* radii, void* geom, eogs_forward_info* info_dev,
+                          eogs_forward_info* info_host)
+{
+    if (int rc = check_common(P, W, H, channels)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!colors) { set_error("For non-RGB, provide precomputed Gaussian colors!"); return -4; }   // rasterizer_impl.cu:244-247
+    if (!cov3D_precomp && (!scales || !rotations)) { set_error("need scales+rotations or cov3D_precomp"); return -4; }
+    if (!means3D || !opacities || !viewmatrix || !radii || !geom || !info_dev) { set_error("null argument"); return -4; }
+    EOGS_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(eogs_forward_info), s));
+    if (P > 0) {
+        const GeomLayout L = geom_layout(P);
+        char* g = static_cast<char*>(geom);
+        if (int rc = launch_preprocess_fwd(s, P, W, H, channels, means3D, scales, rotations, cov3D_precomp,
+                                           opacities, colors, viewmatrix, scale_modifier, antialiasing != 0,
+                                           radii, g, L, info_dev)) return rc;
+        if (int rc = launch_depth_order(s, P, g, L, info_dev)) return rc;
+    }
+    if (info_host)
+        EOGS_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(eogs_forward_info), cudaMemcpyDeviceToHost, s));
+    return 0;
+}
+
+EOGS_API int eogs_forward_render(eogs_stream_t stream, int P, int W, int H, int channels,
+                        uint32_t num_instances, const void* geom, uint32_t* point_list,
+                        void* binning, void* image, const float* bg,
+                        float* out_color, float* out_invdepth)
+{
+    if (int rc = check_common(P, W, H, channels)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!geom || !image || !bg || !out_color) { set_error("null argument"); return -4; }
+    if (num_instances > 0 && (!point_list || !binning)) { set_error("null binning buffers"); return -4; }
+    const GeomLayout GL = geom_layout(P);
+    const ImageLayout IL = image_layout(W, H);
+    const BinningLayout BL = binning_layout(W, H, num_instances);
+    if (int rc = launch_binning(s, P, W, H, num_instances, static_cast<const char*>(geom), GL, point_list,
+                                static_cast<char*>(binning), BL, static_cast<char*>(image), IL)) return rc;
+    return launch_blend_fwd(s, W, H, channels, static_cast<const char*>(geom), GL, point_list,
+                            static_cast<char*>(image), IL, bg, out_color, out_invdepth);
+}
+
+EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, int channels,
+                           const float* means3D, const float* scales, const float* rotations,
+                           const float* cov3D_precomp, const float* opacities, const float* colors,
+                           const float* viewmatrix, float scale_modifier, int antialiasing,
+                           const float* bg, eogs_alloc_fn alloc, void* user,
+                           int32_t* radii, float* out_color, float* out_invdepth,
+                           void** geom, uint32_t** point_list, void** image,
+                           uint32_t* num_instances)
+{
+    if (int rc = check_common(P, W, H, channels)) return rc;
+    if (!alloc || !geom || !point_list || !image || !num_instances) { set_error("null argument"); return -4; }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    *geom = alloc(user, 0, eogs_geom_bytes(P) + 256);
+    *image = alloc(user, 2, eogs_image_bytes(W, H));
+    if (!*geom || !*image) { set_error("allocation callback returned NULL"); return -5; }
+    // the info words live in the tail of the geometry buffer
+    eogs_forward_info* info_dev = reinterpret_cast<eogs_forward_info*>(static_cast<char*>(*geom) + eogs_geom_bytes(P));
+    eogs_forward_info info_host = {0u, 0u};
+    if (int rc = eogs_forward_geometry(stream, P, W, H, channels, means3D, scales, rotations, cov3D_precomp,
+                                       opacities, colors, viewmatrix, scale_modifier, antialiasing, radii,
+                                       *geom, info_dev, nullptr)) return rc;
+    EOGS_CUDA(cudaMemcpyAsync(&info_host, info_dev, sizeof(info_host), cudaMemcpyDeviceToHost, s));
+    EOGS_CUDA(cudaStreamSynchronize(s));
+    if (info_host.error & EOGS_ERR_ALTITUDE_ABOVE_200) {
+        set_error("Point is too high: altitude above 200 (reference: __trap, forward.cu:267-272)");
+        return -6;
+    }
+    *num_instances = info_host.num_instances;
+    void* binning = nullptr;
+    *point_list = nullptr;
+    if (info_host.num_instances > 0) {
+        *point_list = static_cast<uint32_t*>(alloc(user, 3, (size_t)info_host.num_instances * 4));
+        binning = alloc(user, 1, eogs_binning_bytes(W, H, info_host.num_instances));
+        if (!*point_list || !binning) { set_error("allocation callback returned NULL"); return -5; }
+    }
+    return eogs_forward_render(stream, P, W, H, channels, info_host.num_instances, *geom, *point_list,
+                               binning, *image, bg, out_color, out_invdepth);
+}
+
+EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channels,
+                  uint32_t num_instances,
+                  const float* means3D, const float* scales, const float* rotations,
+                  const float* cov3D_precomp, const float* opacities, const float* colors,
+                  const float* viewmatrix, const float* projmatrix,
+                  float scale_modifier, int antialiasing, const float* bg,
+                  const int32_t* radii, const void* geom, const uint32_t* point_list,
+                  const void* image, const float* dL_dpix, const float* dL_dinvdepth,
+                  float* grad_scratch,
+                  float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                  float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                  float* dL_drotations, float* cam_sums)
+{
+    (void)colors;
+    if (int rc = check_common(P, W, H, channels)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!cam_sums) { set_error("null argument"); return -4; }
+    if (P == 0) { EOGS_CUDA(cudaMemsetAsync(cam_sums, 0, 16 * sizeof(float), s)); return 0; }
+    if (!means3D || !opacities || !viewmatrix || !projmatrix || !bg || !radii || !geom || !image || !dL_dpix ||
+        !grad_scratch || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dmeans3D) {
+        set_error("null argument"); return -4;
+    }
+    if (!cov3D_precomp && (!scales || !rotations)) { set_error("need scales+rotations or cov3D_precomp"); return -4; }
+    const GeomLayout GL = geom_layout(P);
+    const ImageLayout IL = image_layout(W, H);
+    EOGS_CUDA(cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s));
+    if (num_instances > 0) {
+        if (!point_list) { set_error("null point_list"); return -4; }
+        if (int rc = launch_blend_bwd(s, W, H, channels, static_cast<const char*>(geom), GL, point_list,
+                                      static_cast<const char*>(image), IL, bg, dL_dpix, dL_dinvdepth,
+                                      grad_scratch)) return rc;
+    }
+    return launch_preprocess_bwd(s, P, W, H, channels, means3D, scales, rotations, cov3D_precomp, opacities,
+                                 viewmatrix, projmatrix, scale_modifier, antialiasing != 0, radii, grad_scratch,
+                                 dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales,
+                                 dL_drotations, cam_sums);
+}
+
+EOGS_API int eogs_mark_visible(eogs_stream_t stream, int P, const float* means3D,
+                      const float* viewmatrix, const float* projmatrix, uint8_t* present)
+{
+    (void)means3D; (void)viewmatrix; (void)projmatrix;
+    if (P < 0) { set_error("bad P"); return -1; }
+    if (P == 0) return 0;
+    if (!present) { set_error("null argument"); return -4; }
+    fill_u8_kernel<<<(P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(present, P, 1);
+    EOGS_LAUNCH_CHECK("fill_u8_kernel");
+    return 0;
+}
+
+EOGS_API int eogs_export_state(eogs_stream_t stream, int P, int W, int H, uint32_t num_instances,
+                      const void* geom, const uint32_t* point_list, const void* image,
+                      float* means2D, float* depths, float* conic_opacity,
+                      uint32_t* tiles_touched, uint64_t* keys_sorted,
+                      uint32_t* ranges, float* final_T, uint32_t* n_contrib)
+{
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const GeomLayout GL = geom_layout(P);
+    const ImageLayout IL = image_layout(W, H);
+    const char* g = static_cast<const char*>(geom);
+    const char* im = static_cast<const char*>(image);
+    const uint32_t tiles = (uint32_t)((W + TILE - 1) / TILE) * (uint32_t)((H + TILE - 1) / TILE);
+    if (P > 0 && (means2D || depths || conic_opacity || tiles_touched)) {
+        export_geom_kernel<<<(P + 255) / 256, 256, 0, s>>>(
+            P, reinterpret_cast<const float4*>(g + GL.splat), reinterpret_cast<const float*>(g + GL.depth),
+            reinterpret_cast<const uint32_t*>(g + GL.tiles), means2D, depths, conic_opacity, tiles_touched);
+        EOGS_LAUNCH_CHECK("export_geom_kernel");
+    }
+    if (keys_sorted && num_instances > 0) {
+        export_keys_kernel<<<tiles, 128, 0, s>>>(tiles, reinterpret_cast<const uint2*>(im + IL.ranges), point_list,
+                                                  reinterpret_cast<const float*>(g + GL.depth), keys_sorted);
+        EOGS_LAUNCH_CHECK("export_keys_kernel");
+    }
+    if (ranges) EOGS_CUDA(cudaMemcpyAsync(ranges, im + IL.ranges, (size_t)tiles * 8, cudaMemcpyDeviceToDevice, s));
+    if (final_T) EOGS_CUDA(cudaMemcpyAsync(final_T, im + IL.final_T, (size_t)W * H * 4, cudaMemcpyDeviceToDevice, s));
+    if (n_contrib) EOGS_CUDA(cudaMemcpyAsync(n_contrib, im + IL.n_contrib, (size_t)W * H * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+}  // extern "C"

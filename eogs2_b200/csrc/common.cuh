@@ -1,0 +1,133 @@
+// Shared definitions of the sm_100a rasterizer kernels (internal; the public surface is
+// include/eogs_raster.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/eogs_raster.h"
+
+namespace eogs {
+
+constexpr int TILE = EOGS_TILE;          // 16x16 pixel tiles (key parity with DGR config.h:15-16)
+constexpr int TILE_PIXELS = TILE * TILE;
+constexpr int REC_F4 = 3;                // float4s per packed splat record (48 bytes)
+constexpr int GRAD_STRIDE = 16;          // floats per Gaussian in the blend-backward gradient record
+
+// ---- packed per-Gaussian splat record (what the blend kernels gather) -----------------
+//   rec[0] = { mean2D.x, mean2D.y, conic.x, conic.y }
+//   rec[1] = { conic.z, opacity*aa_scale, color0, color1 }
+//   rec[2] = { color2, color3, color4, 1/depth }
+// One 48-byte record = 1.5 sectors; a gather touches exactly two 32-byte sectors, versus
+// four separate arrays (means2D, conic_opacity, colors, depths) in the reference.
+
+// ---- opaque buffer layouts -------------------------------------------------------------
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct GeomLayout {
+    size_t splat;        // float4[3P]
+    size_t depth;        // float[P]     200 - altitude (garbage-free: culled entries hold +inf bits)
+    size_t rect;         // uint2[P]     (x0 | y0<<16, x1 | y1<<16) tile rect, exclusive max
+    size_t tiles;        // u32[P]       tiles touched
+    size_t key_in;       // u32[P]       depth bits (culled: 0xFFFFFFFF)
+    size_t key_out;      // u32[P]
+    size_t id_in;        // u32[P]       0..P-1
+    size_t order;        // u32[P]       Gaussian ids sorted by (depth bits, id)
+    size_t offsets;      // u32[P]       inclusive scan of tiles[order[i]]
+    size_t temp;         // CUB temp storage (depth sort, scan)
+    size_t temp_bytes;
+    size_t total;
+};
+
+struct ImageLayout {
+    size_t final_T;      // float[W*H]
+    size_t n_contrib;    // u32[W*H]
+    size_t ranges;       // uint2[tiles]
+    size_t total;
+};
+
+struct BinningLayout {
+    size_t key_in;       // u32[I] tile id per instance (emission order)
+    size_t key_out;      // u32[I]
+    size_t val_in;       // u32[I] Gaussian id per instance
+    size_t temp;
+    size_t temp_bytes;
+    size_t total;
+};
+
+size_t sort_temp_bound(size_t n);
+GeomLayout geom_layout(int P);
+ImageLayout image_layout(int W, int H);
+BinningLayout binning_layout(int W, int H, uint32_t I);
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define EOGS_CUDA(expr)                                             \
+    do {                                                            \
+        cudaError_t _e = (expr);                                    \
+        if (_e != cudaSuccess) return eogs::cuda_fail(_e, #expr);   \
+    } while (0)
+
+#define EOGS_LAUNCH_CHECK(name)                                     \
+    do {                                                            \
+        cudaError_t _e = cudaGetLastError();                        \
+        if (_e != cudaSuccess) return eogs::cuda_fail(_e, name);    \
+    } while (0)
+
+// ---- stage launchers (one per .cu) --------------------------------------------------------
+int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, int channels,
+                          const float* means3D, const float* scales, const float* rotations,
+                          const float* cov3D_precomp, const float* opacities, const float* colors,
+                          const float* view, float scale_modifier, bool antialiasing,
+                          int32_t* radii, char* geom, const GeomLayout& L, eogs_forward_info* info_dev);
+
+int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
+                       eogs_forward_info* info_dev);
+
+int launch_binning(cudaStream_t s, int P, int W, int H, uint32_t I, const char* geom,
+                   const GeomLayout& GL, uint32_t* point_list, char* binning,
+                   const BinningLayout& BL, char* image, const ImageLayout& IL);
+
+int launch_blend_fwd(cudaStream_t s, int W, int H, int channels, const char* geom,
+                     const GeomLayout& GL, const uint32_t* point_list, char* image,
+                     const ImageLayout& IL, const float* bg, float* out_color, float* out_invdepth);
+
+int launch_blend_bwd(cudaStream_t s, int W, int H, int channels, const char* geom,
+                     const GeomLayout& GL, const uint32_t* point_list, const char* image,
+                     const ImageLayout& IL, const float* bg, const float* dL_dpix,
+                     const float* dL_dinvdepth, float* grad_rec);
+
+int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels,
+                          const float* means3D, const float* scales, const float* rotations,
+                          const float* cov3D_precomp, const float* opacities,
+                          const float* view, const float* proj, float scale_modifier,
+                          bool antialiasing, const int32_t* radii, const float* grad_rec,
+                          float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                          float* dL_drotations, float* cam_sums);
+
+// ---- device helpers ---------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Pixel owned by a thread of a 256-thread tile block.  A warp covers an 8x4 pixel patch
+// (not the reference's 16x2 strip): a more compact footprint makes whole-warp skips of
+// non-overlapping Gaussians and warp-coherent early termination more likely.  The mapping
+// is internal — per-pixel results do not depend on it.
+__device__ __forceinline__ void tile_pixel(uint32_t tid, uint32_t& lx, uint32_t& ly) {
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    lx = ((warp & 1u) << 3) | (lane & 7u);
+    ly = ((warp >> 1) << 2) | (lane >> 3);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#endif
+
+}  // namespace eogs

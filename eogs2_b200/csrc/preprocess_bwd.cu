@@ -1,0 +1,241 @@
+// Backward of the geometry stage, one thread per Gaussian, fused into ONE kernel:
+//   computeCov2DCUDA          (DGR/cuda_rasterizer/backward.cu:147-327)
+//   preprocessCUDA<5> backward (backward.cu:400-454) with computeCov3D backward (:331-394)
+//   the three torch reductions of _RasterizeGaussians.backward that build grad_viewmatrix
+//   (DGR/diff_gaussian_rasterization/__init__.py:174-202), as in-kernel block reductions:
+//     cam_sums[0..5]   = sum_p dL_dT[p][0..5]
+//     cam_sums[6..11]  = means3D^T @ dL_dmeans2D[:, :2]   (3x2 row-major)
+//     cam_sums[12..13] = sum_p dL_dmeans2D[p][0..1]
+// so no P x 6 dL_dT tensor, no P x 2 x 2 dL_dconic tensor and no dL_dcov3D tensor (unless the
+// caller passed precomputed covariances) ever reach HBM.
+//
+// dL_dT uses the intended per-Gaussian stride (6*idx + k).  The reference writes dL_dT[idx + k]
+// (backward.cu:320-325), a data race that leaves race-dependent garbage in that term; see
+// DESIGN.md "carve-outs".
+//
+// HBM-bound streaming kernel: 64 B gradient record + 44 B parameters in, 4*(3+C+1+3+3+4) B out.
+#include "common.cuh"
+#include "geom_math.cuh"
+
+namespace eogs {
+
+constexpr int PBW_THREADS = 256;
+constexpr int NSUMS = 14;
+
+template <int C>
+__global__ void __launch_bounds__(PBW_THREADS)
+preprocess_bwd_kernel(int P, int W, int H,
+                      const float* __restrict__ means3D, const float* __restrict__ scales,
+                      const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
+                      const float* __restrict__ opacities, const float* __restrict__ view,
+                      const float* __restrict__ proj, float scale_modifier, bool antialiasing,
+                      const int32_t* __restrict__ radii, const float4* __restrict__ grad_rec,
+                      float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors,
+                      float* __restrict__ dL_dopacity, float* __restrict__ dL_dmeans3D,
+                      float* __restrict__ dL_dcov3D, float* __restrict__ dL_dscales,
+                      float4* __restrict__ dL_drotations, float* __restrict__ cam_sums)
+{
+    __shared__ float s_view[16], s_proj[16];
+    __shared__ float s_part[PBW_THREADS / 32][NSUMS];
+    if (threadIdx.x < 16) {
+        s_view[threadIdx.x] = __ldg(view + threadIdx.x);
+        s_proj[threadIdx.x] = __ldg(proj + threadIdx.x);
+    }
+    __syncthreads();
+
+    const int idx = blockIdx.x * PBW_THREADS + threadIdx.x;
+    float sums[NSUMS];
+#pragma unroll
+    for (int k = 0; k < NSUMS; k++) sums[k] = 0.f;
+
+    if (idx < P) {
+        float g_mean2D[2] = {0.f, 0.f}, g_col[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, g_op = 0.f;
+        float g_mean3D[3] = {0.f, 0.f, 0.f}, g_cov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float g_scale[3] = {0.f, 0.f, 0.f};
+        float4 g_rot = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        if (__ldg(radii + idx) > 0) {
+            const float4 ga = __ldg(grad_rec + (size_t)idx * (GRAD_STRIDE / 4));
+            const float4 gb = __ldg(grad_rec + (size_t)idx * (GRAD_STRIDE / 4) + 1);
+            const float4 gc = __ldg(grad_rec + (size_t)idx * (GRAD_STRIDE / 4) + 2);
+            g_mean2D[0] = ga.x; g_mean2D[1] = ga.y;
+            const float dcon_x = ga.z, dcon_y = ga.w, dcon_w = gb.x;
+            g_op = gb.y;
+            g_col[0] = gb.z; g_col[1] = gb.w; g_col[2] = gc.x; g_col[3] = gc.y; g_col[4] = gc.z;
+
+            const float mx = __ldg(means3D + 3 * (size_t)idx), my = __ldg(means3D + 3 * (size_t)idx + 1),
+                        mz = __ldg(means3D + 3 * (size_t)idx + 2);
+
+            // ---- recompute Sigma3D, T, Sigma2D exactly as the forward did ----
+            float c3[6];
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            float sx = 0.f, sy = 0.f, sz = 0.f;
+            Rot3 R;
+            Mat3 M;
+            if (cov3D_precomp) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) c3[k] = __ldg(cov3D_precomp + 6 * (size_t)idx + k);
+            } else {
+                q = __ldg(rotations + idx);
+                sx = __fmul_rn(scale_modifier, __ldg(scales + 3 * (size_t)idx));
+                sy = __fmul_rn(scale_modifier, __ldg(scales + 3 * (size_t)idx + 1));
+                sz = __fmul_rn(scale_modifier, __ldg(scales + 3 * (size_t)idx + 2));
+                R = quat_to_R(q.x, q.y, q.z, q.w);
+                M = scale_rot(sx, sy, sz, R);
+                cov3d_from_M(M, c3);
+            }
+            const Affine2x3 T = make_T(s_view, W, H);
+            float c_xx, c_xy, c_yy;
+            cov2d_from_cov3d(T, c3, c_xx, c_xy, c_yy);
+
+            // ---- computeCov2DCUDA (backward.cu:198-251) ----
+            constexpr float h_var = 0.3f;
+            float dL_dc_xx = 0.f, dL_dc_xy = 0.f, dL_dc_yy = 0.f;
+            if (antialiasing) {
+                const float det_cov = c_xx * c_yy - c_xy * c_xy;
+                c_xx += h_var; c_yy += h_var;
+                const float det_plus = c_xx * c_yy - c_xy * c_xy;
+                const float ratio = det_cov / det_plus;
+                const float h_scale = sqrtf(fmaxf(0.000025f, ratio));
+                const float d_h = g_op * __ldg(opacities + idx);
+                g_op = g_op * h_scale;
+                const float d_inside_root = ratio <= 0.000025f ? 0.f : d_h / (2.f * h_scale);
+                const float x = c_xx, y = c_yy, z = c_xy, w = h_var;
+                const float den = w * w + w * (x + y) + x * y - z * z;
+                const float denom_f = d_inside_root / (den * den);
+                dL_dc_xx = w * (w * y + y * y + z * z) * denom_f;
+                dL_dc_yy = w * (w * x + x * x + z * z) * denom_f;
+                dL_dc_xy = -2.f * w * z * (w + x + y) * denom_f;
+            } else {
+                c_xx += h_var; c_yy += h_var;
+            }
+            const float denom = c_xx * c_yy - c_xy * c_xy;
+            const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+            if (denom2inv != 0.f) {
+                dL_dc_xx += denom2inv * (-c_yy * c_yy * dcon_x + 2.f * c_xy * c_yy * dcon_y + (denom - c_xx * c_yy) * dcon_w);
+                dL_dc_yy += denom2inv * (-c_xx * c_xx * dcon_w + 2.f * c_xx * c_xy * dcon_y + (denom - c_xx * c_yy) * dcon_x);
+                dL_dc_xy += denom2inv * 2.f * (c_xy * c_yy * dcon_x - (denom + 2.f * c_xy * c_xy) * dcon_y + c_xx * c_xy * dcon_w);
+                g_cov[0] = T.t00 * T.t00 * dL_dc_xx + T.t00 * T.t10 * dL_dc_xy + T.t10 * T.t10 * dL_dc_yy;
+                g_cov[3] = T.t01 * T.t01 * dL_dc_xx + T.t01 * T.t11 * dL_dc_xy + T.t11 * T.t11 * dL_dc_yy;
+                g_cov[5] = T.t02 * T.t02 * dL_dc_xx + T.t02 * T.t12 * dL_dc_xy + T.t12 * T.t12 * dL_dc_yy;
+                g_cov[1] = 2.f * T.t00 * T.t01 * dL_dc_xx + (T.t00 * T.t11 + T.t01 * T.t10) * dL_dc_xy + 2.f * T.t10 * T.t11 * dL_dc_yy;
+                g_cov[2] = 2.f * T.t00 * T.t02 * dL_dc_xx + (T.t00 * T.t12 + T.t02 * T.t10) * dL_dc_xy + 2.f * T.t10 * T.t12 * dL_dc_yy;
+                g_cov[4] = 2.f * T.t02 * T.t01 * dL_dc_xx + (T.t01 * T.t12 + T.t02 * T.t11) * dL_dc_xy + 2.f * T.t11 * T.t12 * dL_dc_yy;
+            }
+
+            // ---- dL_dT, upper 2x3 of T (backward.cu:270-281), reduced over Gaussians ----
+            const float tv0 = T.t00 * c3[0] + T.t01 * c3[1] + T.t02 * c3[2];   // row 0 of T times Vrk columns
+            const float tv1 = T.t00 * c3[1] + T.t01 * c3[3] + T.t02 * c3[4];
+            const float tv2 = T.t00 * c3[2] + T.t01 * c3[4] + T.t02 * c3[5];
+            const float uv0 = T.t10 * c3[0] + T.t11 * c3[1] + T.t12 * c3[2];   // row 1
+            const float uv1 = T.t10 * c3[1] + T.t11 * c3[3] + T.t12 * c3[4];
+            const float uv2 = T.t10 * c3[2] + T.t11 * c3[4] + T.t12 * c3[5];
+            sums[0] = 2.f * tv0 * dL_dc_xx + uv0 * dL_dc_xy;
+            sums[1] = 2.f * tv1 * dL_dc_xx + uv1 * dL_dc_xy;
+            sums[2] = 2.f * tv2 * dL_dc_xx + uv2 * dL_dc_xy;
+            sums[3] = 2.f * uv0 * dL_dc_yy + tv0 * dL_dc_xy;
+            sums[4] = 2.f * uv1 * dL_dc_yy + tv1 * dL_dc_xy;
+            sums[5] = 2.f * uv2 * dL_dc_yy + tv2 * dL_dc_xy;
+
+            // ---- mean: dL_dmean3D = A_2x3^T dL_dmean2D, with projmatrix (backward.cu:439-445) ----
+            const float gx = g_mean2D[0], gy = g_mean2D[1];
+            g_mean3D[0] = s_proj[0] * gx + s_proj[1] * gy;
+            g_mean3D[1] = s_proj[4] * gx + s_proj[5] * gy;
+            g_mean3D[2] = s_proj[8] * gx + s_proj[9] * gy;
+            sums[6] = mx * gx;  sums[7] = mx * gy;
+            sums[8] = my * gx;  sums[9] = my * gy;
+            sums[10] = mz * gx; sums[11] = mz * gy;
+            sums[12] = gx;      sums[13] = gy;
+
+            // ---- computeCov3D backward (backward.cu:331-394) ----
+            if (!cov3D_precomp) {
+                const float dS[3][3] = {{g_cov[0], 0.5f * g_cov[1], 0.5f * g_cov[2]},
+                                        {0.5f * g_cov[1], g_cov[3], 0.5f * g_cov[4]},
+                                        {0.5f * g_cov[2], 0.5f * g_cov[4], g_cov[5]}};
+                const float Mm[3][3] = {{M.m00, M.m01, M.m02}, {M.m10, M.m11, M.m12}, {M.m20, M.m21, M.m22}};   // [c][k]
+                const float Rm[3][3] = {{R.r00, R.r01, R.r02}, {R.r10, R.r11, R.r12}, {R.r20, R.r21, R.r22}};
+                const float s[3] = {sx, sy, sz};
+                // dL_dM[c][k] = 2 * sum_m M[m][k] * dS[c][m];   D[k][c] = s_k * dL_dM[c][k] = dL/dR[c][k]
+                float D[3][3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    float gs = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const float dM = 2.f * (Mm[0][k] * dS[c][0] + Mm[1][k] * dS[c][1] + Mm[2][k] * dS[c][2]);
+                        gs += Rm[c][k] * dM;
+                        D[k][c] = s[k] * dM;
+                    }
+                    g_scale[k] = gs;
+                }
+                const float r = q.x, x = q.y, y = q.z, z = q.w;
+                g_rot.x = 2.f * z * (D[0][1] - D[1][0]) + 2.f * y * (D[2][0] - D[0][2]) + 2.f * x * (D[1][2] - D[2][1]);
+                g_rot.y = 2.f * y * (D[1][0] + D[0][1]) + 2.f * z * (D[2][0] + D[0][2]) + 2.f * r * (D[1][2] - D[2][1]) - 4.f * x * (D[2][2] + D[1][1]);
+                g_rot.z = 2.f * x * (D[1][0] + D[0][1]) + 2.f * r * (D[2][0] - D[0][2]) + 2.f * z * (D[1][2] + D[2][1]) - 4.f * y * (D[2][2] + D[0][0]);
+                g_rot.w = 2.f * r * (D[0][1] - D[1][0]) + 2.f * x * (D[2][0] + D[0][2]) + 2.f * y * (D[1][2] + D[2][1]) - 4.f * z * (D[1][1] + D[0][0]);
+            }
+        }
+
+        dL_dmeans2D[3 * (size_t)idx] = g_mean2D[0];
+        dL_dmeans2D[3 * (size_t)idx + 1] = g_mean2D[1];
+        dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) dL_dcolors[C * (size_t)idx + ch] = g_col[ch];
+        dL_dopacity[idx] = g_op;
+#pragma unroll
+        for (int k = 0; k < 3; k++) dL_dmeans3D[3 * (size_t)idx + k] = g_mean3D[k];
+        if (dL_dcov3D) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) dL_dcov3D[6 * (size_t)idx + k] = g_cov[k];
+        }
+        if (dL_dscales) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) dL_dscales[3 * (size_t)idx + k] = g_scale[k];
+        }
+        if (dL_drotations) dL_drotations[idx] = g_rot;
+    }
+
+    // ---- block reduction of the 14 camera sums: shuffle tree, then one atomic per block ----
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NSUMS; k++) {
+        float v = sums[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) s_part[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NSUMS) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < PBW_THREADS / 32; w++) v += s_part[w][threadIdx.x];
+        if (v != 0.f) atomicAdd(cam_sums + threadIdx.x, v);
+    }
+}
+
+int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels,
+                          const float* means3D, const float* scales, const float* rotations,
+                          const float* cov3D_precomp, const float* opacities,
+                          const float* view, const float* proj, float scale_modifier,
+                          bool antialiasing, const int32_t* radii, const float* grad_rec,
+                          float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                          float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                          float* dL_drotations, float* cam_sums)
+{
+    EOGS_CUDA(cudaMemsetAsync(cam_sums, 0, 16 * sizeof(float), s));
+    const int blocks = (P + PBW_THREADS - 1) / PBW_THREADS;
+    auto run = [&](auto kernel) {
+        kernel<<<blocks, PBW_THREADS, 0, s>>>(
+            P, W, H, means3D, scales, reinterpret_cast<const float4*>(rotations), cov3D_precomp,
+            opacities, view, proj, scale_modifier, antialiasing, radii,
+            reinterpret_cast<const float4*>(grad_rec), dL_dmeans2D, dL_dcolors, dL_dopacity,
+            dL_dmeans3D, dL_dcov3D, dL_dscales, reinterpret_cast<float4*>(dL_drotations), cam_sums);
+    };
+    if (channels == 5) run(preprocess_bwd_kernel<5>);
+    else if (channels == 3) run(preprocess_bwd_kernel<3>);
+    else { set_error("channels must be 3 or 5, got %d", channels); return -1; }
+    EOGS_LAUNCH_CHECK("preprocess_bwd_kernel");
+    return 0;
+}
+
+}  // namespace eogs

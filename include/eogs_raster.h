@@ -1,0 +1,183 @@
+/*
+ * eogs_raster.h — C ABI of libeogs_raster.so, the B200 (sm_100a) affine-camera
+ * Gaussian-splatting rasterizer that stands in for EOGS++'s
+ * diff-gaussian-rasterization extension ("DGR" below =
+ * src/gaussiansplatting/submodules/diff-gaussian-rasterization of gardiens/EOGS2).
+ *
+ * Boundary rules
+ *   - extern "C", plain pointers and sizes only; no torch / C++ types.
+ *   - Every pointer marked "dev" is a CUDA device pointer owned by the caller
+ *     (torch owns every buffer, as in DGR/rasterize_points.cu:69-85,163-174).
+ *     The library never allocates or frees device memory.
+ *   - Every call enqueues work on the given stream and returns without
+ *     synchronising, except where stated.  No global mutable state: calls on
+ *     different streams / devices are independent.
+ *   - Return value: 0 = ok, <0 = argument error, >0 = cudaError_t.
+ *     eogs_last_error() returns a thread-local message for the last failure.
+ *
+ * What each entry point replaces in the reference
+ *   eogs_forward_geometry + eogs_forward_render
+ *        = _C.rasterize_gaussians            (DGR/ext.cpp:16, DGR/rasterize_points.cu:35-124,
+ *                                             CudaRasterizer::Rasterizer::forward,
+ *                                             DGR/cuda_rasterizer/rasterizer_impl.cu:198-341)
+ *   eogs_rasterize_forward (single call with allocation callbacks)
+ *        = the same, in the shape of Rasterizer::forward's std::function<char*(size_t)>
+ *          resize callbacks (DGR/cuda_rasterizer/rasterizer.h:31-56)
+ *   eogs_backward
+ *        = _C.rasterize_gaussians_backward   (DGR/ext.cpp:17, DGR/rasterize_points.cu:126-224,
+ *                                             Rasterizer::backward, rasterizer_impl.cu:345-452)
+ *          plus the three torch reductions of _RasterizeGaussians.backward
+ *          (DGR/diff_gaussian_rasterization/__init__.py:174-202), returned as 14 sums.
+ *   eogs_mark_visible
+ *        = _C.mark_visible                   (DGR/ext.cpp:18, rasterize_points.cu:226-245)
+ *
+ * The forward is split in two because the number of (Gaussian, tile) instances is
+ * only known after the geometry stage; the reference hides the same dependency
+ * behind a blocking cudaMemcpy (rasterizer_impl.cu:284).
+ */
+#ifndef EOGS_RASTER_H_INCLUDED
+#define EOGS_RASTER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EOGS_API __attribute__((visibility("default")))
+#else
+#define EOGS_API
+#endif
+
+#define EOGS_ABI_VERSION 1
+#define EOGS_TILE 16            /* BLOCK_X = BLOCK_Y = 16, DGR/cuda_rasterizer/config.h:15-16 */
+#define EOGS_MAX_CHANNELS 5     /* NUM_CHANNELS 5,        DGR/cuda_rasterizer/config.h:14    */
+
+/* error bits reported in eogs_forward_info.error */
+#define EOGS_ERR_ALTITUDE_ABOVE_200 1u  /* reference: printf + __trap(), forward.cu:267-272 */
+
+typedef void* eogs_stream_t;    /* cudaStream_t */
+
+/* Host-visible result of the geometry stage (write target must be pinned host memory). */
+typedef struct eogs_forward_info {
+    uint32_t num_instances;     /* I = sum of tiles touched = reference's num_rendered */
+    uint32_t error;             /* EOGS_ERR_* bits */
+} eogs_forward_info;
+
+EOGS_API int eogs_abi_version(void);
+EOGS_API const char* eogs_last_error(void);
+
+/* ---- scratch sizing (host only, no CUDA calls that touch a device) ---------------- */
+/* Per-Gaussian state kept from forward to backward (packed splat records, depths, tile
+ * rects, depth order, offsets) + the temporary space of the depth sort and scan.
+ * Counterpart of required<GeometryState>(P), rasterizer_impl.cu:155-170. */
+EOGS_API size_t eogs_geom_bytes(int P);
+/* Per-image state kept for backward: final transmittance, last contributor, tile ranges.
+ * Counterpart of required<ImageState>(W*H), rasterizer_impl.cu:172-179. */
+EOGS_API size_t eogs_image_bytes(int W, int H);
+/* Temporary space of the tile sort for `num_instances` instances (freed after forward).
+ * Counterpart of required<BinningState>(I), rasterizer_impl.cu:181-194, minus the sorted
+ * Gaussian list, which is the separate `point_list` argument (4*I bytes) because it is
+ * the only part backward needs. */
+EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t num_instances);
+
+/* ---- forward, stage 1: per-Gaussian geometry -------------------------------------- */
+/* Affine projection, 3D->2D covariance, conic, radius, tile rect, depth = 200 - altitude,
+ * depth ordering and instance offsets.  Replaces preprocessCUDA (forward.cu:154-283) and
+ * cub InclusiveSum (rasterizer_impl.cu:280).
+ *   means3D  [P,3]   dev   scales [P,3] / rotations [P,4] dev, or cov3D_precomp [P,6] dev
+ *   opacities[P]     dev   colors [P,channels] dev (colors_precomp; required, as in
+ *                          rasterizer_impl.cu:244-247)
+ *   viewmatrix[16]   dev   transposed [[A,b],[0,1]]: A[r][c] = v[4c+r], b[r] = v[12+r]
+ *   radii    [P] i32 dev   out, 0 for culled Gaussians
+ *   geom            dev   eogs_geom_bytes(P) bytes, 256-byte aligned
+ *   info_dev        dev   8 bytes; info_host: 8 bytes of pinned host memory, filled by an
+ *                          async copy on `stream` — synchronise the stream before reading. */
+EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, int channels,
+                          const float* means3D, const float* scales, const float* rotations,
+                          const float* cov3D_precomp, const float* opacities, const float* colors,
+                          const float* viewmatrix, float scale_modifier, int antialiasing,
+                          int32_t* radii, void* geom, eogs_forward_info* info_dev,
+                          eogs_forward_info* info_host);
+
+/* ---- forward, stage 2: binning + blend --------------------------------------------- */
+/* Instance emission, tile sort, tile ranges, front-to-back alpha blend.  Replaces
+ * duplicateWithKeys, cub SortPairs, identifyTileRanges (rasterizer_impl.cu:70-138,292-321)
+ * and renderCUDA (forward.cu:288-411).
+ *   point_list [I] u32 dev  out: Gaussian ids sorted by (tile, depth bits, id) — identical
+ *                           to the reference's binningState.point_list
+ *   binning          dev    eogs_binning_bytes(W,H,I) bytes of scratch
+ *   image            dev    eogs_image_bytes(W,H) bytes (kept for backward)
+ *   bg [channels]    dev
+ *   out_color [channels,H,W] dev, out_invdepth [H,W] dev (may be NULL) */
+EOGS_API int eogs_forward_render(eogs_stream_t stream, int P, int W, int H, int channels,
+                        uint32_t num_instances, const void* geom, uint32_t* point_list,
+                        void* binning, void* image, const float* bg,
+                        float* out_color, float* out_invdepth);
+
+/* ---- forward, single call with allocation callbacks -------------------------------- */
+/* Same as the two stages back to back; `alloc(user, which, bytes)` must return a device
+ * pointer of at least `bytes` bytes (which: 0 = geom, 1 = binning scratch, 2 = image,
+ * 3 = point_list).  Synchronises `stream` once, like rasterizer_impl.cu:284.
+ * Returns the pointers it obtained through *geom / *point_list / *image so the caller can
+ * hand them to eogs_backward.  *num_instances receives I. */
+typedef void* (*eogs_alloc_fn)(void* user, int which, size_t bytes);
+EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, int channels,
+                           const float* means3D, const float* scales, const float* rotations,
+                           const float* cov3D_precomp, const float* opacities, const float* colors,
+                           const float* viewmatrix, float scale_modifier, int antialiasing,
+                           const float* bg, eogs_alloc_fn alloc, void* user,
+                           int32_t* radii, float* out_color, float* out_invdepth,
+                           void** geom, uint32_t** point_list, void** image,
+                           uint32_t* num_instances);
+
+/* ---- backward ----------------------------------------------------------------------- */
+/* Blend backward + preprocess backward + camera-gradient reductions.
+ *   dL_dpix [channels,H,W] dev; dL_dinvdepth [H,W] dev or NULL
+ *   grad_scratch dev: 16*P floats, zeroed by this call
+ * outputs (all dev, all written by this call; culled Gaussians get zeros):
+ *   dL_dmeans2D [P,3] (z = 0)   dL_dcolors [P,channels]   dL_dopacity [P]
+ *   dL_dmeans3D [P,3]           dL_dcov3D [P,6] or NULL    dL_dscales [P,3] or NULL
+ *   dL_drotations [P,4] or NULL
+ *   cam_sums [16]: [0..5] = sum_p dL_dT[p][0..5]                  (__init__.py:180-192)
+ *                  [6..11] = means3D^T @ dL_dmeans2D[:, :2], row-major 3x2 (__init__.py:195-196)
+ *                  [12..13] = sum_p dL_dmeans2D[p][0..1]          (__init__.py:199-202)
+ *   projmatrix[16] dev: used for dL_dmeans3D like backward.cu:439-445 (pass viewmatrix when
+ *   they are the same tensor). */
+EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channels,
+                  uint32_t num_instances,
+                  const float* means3D, const float* scales, const float* rotations,
+                  const float* cov3D_precomp, const float* opacities, const float* colors,
+                  const float* viewmatrix, const float* projmatrix,
+                  float scale_modifier, int antialiasing, const float* bg,
+                  const int32_t* radii, const void* geom, const uint32_t* point_list,
+                  const void* image, const float* dL_dpix, const float* dL_dinvdepth,
+                  float* grad_scratch,
+                  float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                  float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                  float* dL_drotations, float* cam_sums);
+
+/* ---- markVisible ------------------------------------------------------------------- */
+/* The reference's in_frustum culls nothing for affine cameras (its body is
+ * commented out, auxiliary.h:151-176): every Gaussian is reported visible. */
+EOGS_API int eogs_mark_visible(eogs_stream_t stream, int P, const float* means3D,
+                      const float* viewmatrix, const float* projmatrix, uint8_t* present);
+
+/* ---- inspection (parity tests) ----------------------------------------------------- */
+/* Copies internal state into caller buffers in the reference's layouts so that tests can
+ * compare bit for bit.  Any output pointer may be NULL.
+ *   means2D [P,2], depths [P], conic_opacity [P,4], tiles_touched [P] u32 : geomState fields
+ *   keys_sorted [I] u64 = (tile << 32) | depth bits, rebuilt from point_list
+ *   ranges [tiles,2] u32, final_T [H*W], n_contrib [H*W] u32 : imgState fields */
+EOGS_API int eogs_export_state(eogs_stream_t stream, int P, int W, int H, uint32_t num_instances,
+                      const void* geom, const uint32_t* point_list, const void* image,
+                      float* means2D, float* depths, float* conic_opacity,
+                      uint32_t* tiles_touched, uint64_t* keys_sorted,
+                      uint32_t* ranges, float* final_T, uint32_t* n_contrib);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EOGS_RASTER_H_INCLUDED */
