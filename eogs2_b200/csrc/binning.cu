@@ -93,10 +93,14 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
     // (depth bits, id): keys are non-negative floats, so their bit patterns order like the
     // values; the radix sort is stable and ids come in ascending, which yields the tie order.
     size_t need = 0;
-    EOGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, key_in, key_out, id_in, order, P, 0, 32, s));
+    cub::DoubleBuffer<uint32_t> keys(key_in, key_out);
+    cub::DoubleBuffer<uint32_t> vals(id_in, order);
+    EOGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, P, 0, 32, s));
     if (need > L.temp_bytes) { set_error("depth sort temp %zu > %zu", need, L.temp_bytes); return -3; }
     need = L.temp_bytes;
-    EOGS_CUDA(cub::DeviceRadixSort::SortPairs(temp, need, key_in, key_out, id_in, order, P, 0, 32, s));
+    EOGS_CUDA(cub::DeviceRadixSort::SortPairs(temp, need, keys, vals, P, 0, 32, s));
+    if (vals.Current() != order)
+        EOGS_CUDA(cudaMemcpyAsync(order, vals.Current(), (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
 
     auto in = thrust::make_transform_iterator(static_cast<const uint32_t*>(order), GatherTiles{tiles});
     need = 0;
