@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd affine renders/sec of the EOGS++ rasterizer path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json `metric`): one "step" = one forward + backward rasterisation of a
+synthetic 1 M-Gaussian scene ("trained-like") through a 2048x2048 affine camera,
+5 channels (RGB, altitude, opacity) + inverse depth, dense upstream gradient, gradients to all
+Gaussian parameters and to the affine camera matrix.
+
+  value     renders/s over all ranks, inputs resident in HBM, device-timed (CUDA events per step,
+            max over ranks), L2 flushed between steps (outside the timed spans).
+  e2e       the same through the public API (diff_gaussian_rasterization.GaussianRasterizer +
+            autograd) with HOST inputs: per step the Gaussian tensors are copied from pinned host
+            memory, and the loss and camera gradient are read back.
+  roofline  dominant kernel (blend backward), algorithmic bytes / measured duration vs measured HBM peak.
+  cpu_baseline  oracle/cpu_splat.py (PyTorch on the host cores) on a bounded tile sample.
+
+--impl reference times the reference rasterizer's own CUDA kernels (oracle/_ref/libeogs_ref.so,
+compiled for sm_100a from /root/reference by oracle/ref_build/Makefile) on the same workload;
+when that library is absent it falls back to the CPU port.  N > 1: data parallel over views —
+each rank renders its own camera and the 14*P-float gradient bucket is all-reduced with NCCL
+inside the step (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+P_GAUSS = 1_000_000
+IMG = 2048
+SEED = 1337
+STAGES = ["", "preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges", "blend_fwd",
+          "bwd_zero", "blend_bwd", "preprocess_bwd"]
+
+
+# ----------------------------------------------------------------------------------------------
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(dev, rank: int):
+    from eogs2_b200 import scene as S
+    sc = S.make_scene(P_GAUSS, "trained", SEED)
+    view = S.make_camera(SEED + rank)                 # one camera per rank (data parallel over views)
+    host = dict(means3D=sc.means3D, scales=sc.scales, rotations=sc.rotations, opacities=sc.opacities,
+                colors=S.colors_precomp(sc, view))
+    host = {k: v.pin_memory() for k, v in host.items()}
+    devt = {k: v.to(dev) for k, v in host.items()}
+    dcol, dinv = S.upstream_grads(5, IMG, IMG, SEED + rank, False)
+    return dict(host=host, dev=devt, view=view.to(dev), view_host=view, bg=S.background(SEED).to(dev),
+                dcol=dcol.to(dev), dinv=dinv.to(dev), sc=sc)
+
+
+class L2Flusher:
+    def __init__(self, dev):
+        self.buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def __call__(self):
+        self.buf.fill_(1)
+
+
+# ----------------------------------------------------------------------------------------------
+# step functions
+def ours_step_factory(wl, dev):
+    import eogs2_b200 as E
+    d = wl["dev"]
+    empty = torch.empty(0, device=dev)
+
+    def step():
+        st = E.rasterize_forward_raw(wl["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"],
+                                     d["rotations"], 1.0, empty, wl["view"], IMG, IMG, False, False)
+        g = E.rasterize_backward_raw(st, wl["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"],
+                                     d["rotations"], 1.0, empty, wl["view"], wl["view"], wl["dcol"], wl["dinv"])
+        return st, g
+    return step
+
+
+def ours_e2e_factory(wl, dev):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    h = wl["host"]
+    names = ["means3D", "scales", "rotations", "opacities", "colors"]
+    h2d = sum(h[k].numel() * 4 for k in names)
+    out_host = torch.zeros(17, dtype=torch.float32).pin_memory()
+
+    def step():
+        t = {k: h[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
+        view = wl["view"].clone().requires_grad_(True)
+        settings = GaussianRasterizationSettings(
+            image_height=IMG, image_width=IMG, tanfovx=1.0, tanfovy=1.0, bg=wl["bg"], scale_modifier=1.0,
+            viewmatrix=view, projmatrix=view, sh_degree=0, campos=torch.zeros(3, device=dev), prefiltered=False,
+            debug=False, antialiasing=False)
+        means2D = torch.zeros_like(t["means3D"], requires_grad=True)
+        color, radii, invd = GaussianRasterizer(settings)(
+            means3D=t["means3D"], means2D=means2D, opacities=t["opacities"], colors_precomp=t["colors"],
+            scales=t["scales"], rotations=t["rotations"])
+        loss = (color * wl["dcol"]).sum()
+        loss.backward()
+        res = torch.cat([loss.detach().reshape(1), view.grad.reshape(-1)])
+        out_host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(out_host[0])
+    return step, h2d, out_host.numel() * 4
+
+
+def ref_step_factory(wl, dev):
+    from oracle import ref_rasterizer as R
+    d = wl["dev"]
+    empty = torch.empty(0, device=dev)
+    campos = torch.zeros(3, device=dev)
+
+    def step(dd=None):
+        dd = dd or d
+        st = R.forward(wl["bg"], dd["means3D"], dd["colors"], dd["opacities"], dd["scales"], dd["rotations"], 1.0,
+                       empty, wl["view"], wl["view"], 1.0, 1.0, IMG, IMG, campos, False, False)
+        g = R.backward(st, wl["bg"], dd["means3D"], dd["colors"], dd["opacities"], dd["scales"], dd["rotations"],
+                       1.0, empty, wl["view"], wl["view"], 1.0, 1.0, wl["dcol"], wl["dinv"], campos, False)
+        return st, g
+    return step
+
+
+def ref_e2e_factory(wl, dev):
+    from oracle import ref_rasterizer as R
+    h = wl["host"]
+    names = ["means3D", "scales", "rotations", "opacities", "colors"]
+    h2d = sum(h[k].numel() * 4 for k in names)
+    out_host = torch.zeros(17, dtype=torch.float32).pin_memory()
+    inner = ref_step_factory(wl, dev)
+
+    def step():
+        t = {k: h[k].to(dev, non_blocking=True) for k in names}
+        st, g = inner(t)
+        # the Python half of the reference's backward (DGR __init__.py:172-202) and a loss read-back
+        terms = R.grad_viewmatrix_terms(g, t["means3D"], wl["view"], IMG, IMG)
+        loss = (st.color * wl["dcol"]).sum()
+        out_host.copy_(torch.cat([loss.reshape(1), terms["total"].reshape(-1)]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(out_host[0])
+    return step, h2d, out_host.numel() * 4
+
+
+# ----------------------------------------------------------------------------------------------
+def timed_steps(step, steps, warmup, flush, world, post=None):
+    """K steps, each bracketed by CUDA events on the current stream; L2 flushed between steps."""
+    import torch.distributed as dist
+    for _ in range(warmup):
+        step()
+        if post:
+            post()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        flush()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step()
+        if post:
+            post()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    total_ms = sum(s.elapsed_time(e) for s, e in evs)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    return total_ms, wall
+
+
+def cpu_baseline(wl, seconds_hint=20.0):
+    """PyTorch-on-CPU fwd+bwd (oracle/cpu_splat.py) on a bounded sample of the same workload: geometry
+    and binning for all P Gaussians, blend + autograd for a central window of tiles; extrapolated to the
+    full image by tile count."""
+    from oracle import cpu_splat as CS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc = wl["sc"]
+    gx = IMG // 16
+    win = 6                                            # 6x6 = 36 of 16384 tiles
+    tw = (gx // 2 - win // 2, gx // 2 - win // 2, gx // 2 + win // 2, gx // 2 + win // 2)
+    tens = (sc.means3D, sc.scales, sc.rotations, sc.opacities, wl["host"]["colors"])
+    t0 = time.perf_counter()
+    CS.render_fwd_bwd(tens, wl["view_host"], wl["bg"].cpu(), IMG, IMG, wl["dcol"].cpu(), None, False, tile_window=(0, 0, 0, 0))
+    t_geom = time.perf_counter() - t0                  # per-Gaussian work + sort + autograd of it, no tiles
+    t0 = time.perf_counter()
+    CS.render_fwd_bwd(tens, wl["view_host"], wl["bg"].cpu(), IMG, IMG, wl["dcol"].cpu(), None, False, tile_window=tw)
+    t_win = time.perf_counter() - t0
+    per_tile = max(t_win - t_geom, 1e-6) / (win * win)
+    est = t_geom + per_tile * gx * gx
+    return {"value": 1.0 / est, "unit": "renders/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/cpu_splat.py (PyTorch CPU, fp32, autograd): all 1M Gaussians preprocessed+sorted "
+                      f"({t_geom:.1f} s) + {win*win} of {gx*gx} tiles blended fwd+bwd ({t_win - t_geom:.1f} s), "
+                      f"extrapolated by tile count to {est:.0f} s per render"}
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, world, local = dist_env()
+
+    if args.impl == "reference" and rank != 0:
+        return 0                                           # rank 0 alone runs the reference arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ref_world = world
+    if args.impl == "reference":
+        world = 1
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = make_workload(dev, rank)
+    flush = L2Flusher(dev)
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    base = {"metric": "fwd+bwd affine renders/sec at 1M Gaussians 2048^2", "unit": "renders/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2] main view: 1M trained-like Gaussians (seed 1337), one 2048x2048 "
+                                   "affine camera per rank, 5 channels + inverse depth, fwd+bwd with dense upstream "
+                                   "gradient, gradients to all Gaussian parameters and the camera matrix",
+                       "P": P_GAUSS, "W": IMG, "H": IMG, "channels": 5,
+                       "l2": "256 MiB buffer written between timed steps (outside the event spans)",
+                       "parallelism": f"dp{args.gpus} over views" if args.gpus > 1 else "single GPU"}}
+
+    sampler = ClockSampler(local)
+
+    if args.impl == "reference":
+        from oracle import ref_rasterizer as R
+        if not R.available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libeogs_ref.so not built (needs /root/reference at build time)"}))
+            return 0
+        step = ref_step_factory(wl, dev)
+        sampler.start()
+        total_ms, wall = timed_steps(step, args.steps, args.warmup, flush, 1)
+        e2e_step, h2d, d2h = ref_e2e_factory(wl, dev)
+        e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, 1)
+        clocks = sampler.stop()
+        st, _ = step()
+        val = args.steps / (total_ms / 1e3)
+        line = dict(base, impl="reference", n_gpus=1, value=val, ms_per_step=total_ms / args.steps, clocks=clocks,
+                    e2e={"value": args.steps / (e2e_ms / 1e3), "unit": "renders/s", "h2d_bytes_per_step": h2d,
+                         "d2h_bytes_per_step": d2h},
+                    gpu_launches=0,
+                    cpu_baseline={"value": val, "unit": "renders/s", "cores": 0, "kind": "reference",
+                                  "sample": "full workload; the reference has no CPU backend, so this arm runs its own CUDA "
+                                            "kernels (DGR cuda_rasterizer, compiled for sm_100a with nvcc defaults) on the GPU"},
+                    instances=st.num_rendered, requested_gpus=ref_world)
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ ours
+    import eogs2_b200 as E
+    from eogs2_b200 import _cabi
+    lib = _cabi.load()
+    step = ours_step_factory(wl, dev)
+    post = None
+    bucket = None
+    if world > 1:
+        import torch.distributed as dist
+        bucket = torch.empty(14 * P_GAUSS + 16, dtype=torch.float32, device=dev)
+        last = {}
+
+        def step_dp():
+            st, g = step()
+            last["g"] = g
+            return st, g
+
+        def post():
+            # flat fp32 bucket of the Adam groups' gradients (xyz 3, f_dc 3, opacity 1, scaling 3, rotation 4)
+            # + the camera sums, all-reduced over NVLink before the replicated optimiser step
+            g = last["g"]
+            P = P_GAUSS
+            bucket[0:3 * P].view(P, 3).copy_(g[3])                       # dL_dmeans3D
+            bucket[3 * P:6 * P].view(P, 3).copy_(g[1][:, :3])            # dL_dcolors rgb -> f_dc
+            bucket[6 * P:7 * P].view(P, 1).copy_(g[2])                   # dL_dopacity
+            bucket[7 * P:10 * P].view(P, 3).copy_(g[5])                  # dL_dscales
+            bucket[10 * P:14 * P].view(P, 4).copy_(g[6])                 # dL_drotations
+            bucket[14 * P:].copy_(g[7])
+            dist.all_reduce(bucket)
+        run_step = step_dp
+    else:
+        run_step = step
+
+    sampler.start()
+    total_ms, wall = timed_steps(run_step, args.steps, args.warmup, flush, world, post)
+    clocks = sampler.stop()
+
+    # per-stage device times (CUDA events recorded inside the library on the launch stream)
+    lib.eogs_profile_enable(1)
+    stage_ms = [0.0] * len(STAGES)
+    reps = max(3, min(args.steps, 10))
+    buf = (ctypes.c_float * 16)()
+    for _ in range(reps):
+        flush()
+        step()
+        lib.eogs_profile_read(buf, 16)
+        for i in range(len(STAGES)):
+            stage_ms[i] += buf[i] / reps
+    lib.eogs_profile_enable(0)
+    st, g = step()
+    torch.cuda.synchronize()
+    I = st.num_rendered
+
+    # e2e through the public API with host inputs
+    e2e_step, h2d, d2h = ours_e2e_factory(wl, dev)
+    e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, world)
+
+    value = world * args.steps / (total_ms / 1e3)
+    # roofline of the dominant kernel: blend backward.  Algorithmic bytes per launch:
+    # per instance 4 B id + 48 B record gathered + 44 B (11 floats) reduced into the gradient record;
+    # per pixel 4*(C+1) B upstream gradient + 8 B final_T / n_contrib.
+    bwd_bytes = I * (4 + 48 + 44) + IMG * IMG * (4 * 6 + 8)
+    bwd_ms = stage_ms[STAGES.index("blend_bwd")]
+    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
+    line = dict(base, value=value, ms_per_step=total_ms / args.steps, clocks=clocks,
+                e2e={"value": world * args.steps / (e2e_ms / 1e3), "unit": "renders/s",
+                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                gpu_launches=7 * args.steps,
+                roofline={"kernel": "blend_bwd_kernel<5>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                          "ms_per_launch": bwd_ms, "algorithmic_bytes": bwd_bytes,
+                          "note": "blend kernels are FP32-issue/shuffle bound, not HBM bound; see DESIGN.md"},
+                stage_ms={STAGES[i]: round(stage_ms[i], 4) for i in range(1, len(STAGES))},
+                instances=I, wall_s=wall)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(wl)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -102,6 +102,7 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
     if (vals.Current() != order)
         EOGS_CUDA(cudaMemcpyAsync(order, vals.Current(), (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
 
+    prof_mark(s, ST_DEPTH_SORT);
     auto in = thrust::make_transform_iterator(static_cast<const uint32_t*>(order), GatherTiles{tiles});
     need = 0;
     EOGS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, need, in, offsets, P, s));
@@ -111,6 +112,7 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
 
     publish_info_kernel<<<1, 1, 0, s>>>(offsets, P, info_dev);
     EOGS_LAUNCH_CHECK("publish_info_kernel");
+    prof_mark(s, ST_SCAN);
     return 0;
 }
 
@@ -213,6 +215,7 @@ int launch_binning(cudaStream_t s, int P, int W, int H, uint32_t I, const char* 
         reinterpret_cast<const uint32_t*>(geom + GL.offsets),
         reinterpret_cast<const uint2*>(geom + GL.rect), key_in, val_in);
     EOGS_LAUNCH_CHECK("emit_instances_kernel");
+    prof_mark(s, ST_EMIT);
 
     const int bit = (int)higher_msb(tiles);
     cub::DoubleBuffer<uint32_t> keys(key_in, key_out);
@@ -225,8 +228,10 @@ int launch_binning(cudaStream_t s, int P, int W, int H, uint32_t I, const char* 
     if (vals.Current() != point_list)
         EOGS_CUDA(cudaMemcpyAsync(point_list, vals.Current(), (size_t)I * 4, cudaMemcpyDeviceToDevice, s));
 
+    prof_mark(s, ST_TILE_SORT);
     tile_ranges_kernel<<<(I + 255) / 256, 256, 0, s>>>(I, keys.Current(), ranges);
     EOGS_LAUNCH_CHECK("tile_ranges_kernel");
+    prof_mark(s, ST_RANGES);
     return 0;
 }
 

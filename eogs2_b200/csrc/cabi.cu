@@ -21,6 +21,38 @@ int cuda_fail(cudaError_t e, const char* what) {
     return (int)e;
 }
 
+struct Profiler {
+    bool on = false;
+    bool created = false;
+    cudaEvent_t start{};
+    cudaEvent_t ev[ST_COUNT]{};
+    bool seen[ST_COUNT]{};
+    int order[ST_COUNT * 2]{};
+    int n = 0;
+};
+static thread_local Profiler g_prof;
+
+void prof_begin(cudaStream_t s) {
+    Profiler& p = g_prof;
+    if (!p.on) return;
+    if (!p.created) {
+        cudaEventCreate(&p.start);
+        for (int i = 0; i < ST_COUNT; i++) cudaEventCreate(&p.ev[i]);
+        p.created = true;
+    }
+    for (int i = 0; i < ST_COUNT; i++) p.seen[i] = false;
+    p.n = 0;
+    cudaEventRecord(p.start, s);
+}
+
+void prof_mark(cudaStream_t s, int stage) {
+    Profiler& p = g_prof;
+    if (!p.on || !p.created || stage <= 0 || stage >= ST_COUNT || p.seen[stage]) return;
+    p.seen[stage] = true;
+    p.order[p.n++] = stage;
+    cudaEventRecord(p.ev[stage], s);
+}
+
 __global__ void fill_u8_kernel(uint8_t* p, int n, uint8_t v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -68,6 +100,26 @@ extern "C" {
 EOGS_API int eogs_abi_version(void) { return EOGS_ABI_VERSION; }
 EOGS_API const char* eogs_last_error(void) { return g_err; }
 
+// Instrumentation: per-stage device times of the calls made on this thread since the last
+// eogs_profile_enable(1) / eogs_profile_read().  ms[stage] for the Stage enum of common.cuh;
+// stages that did not run read 0.  Synchronises the recorded events.
+EOGS_API int eogs_profile_enable(int on) { g_prof.on = on != 0; return 0; }
+EOGS_API int eogs_profile_read(float* ms, int n) {
+    Profiler& p = g_prof;
+    for (int i = 0; i < n; i++) ms[i] = 0.f;
+    if (!p.created) return 0;
+    cudaEvent_t prev = p.start;
+    for (int k = 0; k < p.n; k++) {
+        const int st = p.order[k];
+        EOGS_CUDA(cudaEventSynchronize(p.ev[st]));
+        float t = 0.f;
+        EOGS_CUDA(cudaEventElapsedTime(&t, prev, p.ev[st]));
+        if (st < n) ms[st] += t;
+        prev = p.ev[st];
+    }
+    return p.n;
+}
+
 EOGS_API size_t eogs_geom_bytes(int P) { return geom_layout(P).total; }
 EOGS_API size_t eogs_image_bytes(int W, int H) { return image_layout(W, H).total; }
 EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t I) { return binning_layout(W, H, I).total; }
@@ -85,12 +137,14 @@ EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, in
     if (!cov3D_precomp && (!scales || !rotations)) { set_error("need scales+rotations or cov3D_precomp"); return -4; }
     if (!means3D || !opacities || !viewmatrix || !radii || !geom || !info_dev) { set_error("null argument"); return -4; }
     EOGS_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(eogs_forward_info), s));
+    prof_begin(s);
     if (P > 0) {
         const GeomLayout L = geom_layout(P);
         char* g = static_cast<char*>(geom);
         if (int rc = launch_preprocess_fwd(s, P, W, H, channels, means3D, scales, rotations, cov3D_precomp,
                                            opacities, colors, viewmatrix, scale_modifier, antialiasing != 0,
                                            radii, g, L, info_dev)) return rc;
+        prof_mark(s, ST_PREPROCESS);
         if (int rc = launch_depth_order(s, P, g, L, info_dev)) return rc;
     }
     if (info_host)
@@ -112,8 +166,10 @@ EOGS_API int eogs_forward_render(eogs_stream_t stream, int P, int W, int H, int 
     const BinningLayout BL = binning_layout(W, H, num_instances);
     if (int rc = launch_binning(s, P, W, H, num_instances, static_cast<const char*>(geom), GL, point_list,
                                 static_cast<char*>(binning), BL, static_cast<char*>(image), IL)) return rc;
-    return launch_blend_fwd(s, W, H, channels, static_cast<const char*>(geom), GL, point_list,
-                            static_cast<char*>(image), IL, bg, out_color, out_invdepth);
+    if (int rc = launch_blend_fwd(s, W, H, channels, static_cast<const char*>(geom), GL, point_list,
+                                  static_cast<char*>(image), IL, bg, out_color, out_invdepth)) return rc;
+    prof_mark(s, ST_BLEND_FWD);
+    return 0;
 }
 
 EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, int channels,
@@ -181,16 +237,20 @@ EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channe
     const GeomLayout GL = geom_layout(P);
     const ImageLayout IL = image_layout(W, H);
     EOGS_CUDA(cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s));
+    prof_mark(s, ST_BWD_ZERO);
     if (num_instances > 0) {
         if (!point_list) { set_error("null point_list"); return -4; }
         if (int rc = launch_blend_bwd(s, W, H, channels, static_cast<const char*>(geom), GL, point_list,
                                       static_cast<const char*>(image), IL, bg, dL_dpix, dL_dinvdepth,
                                       grad_scratch)) return rc;
     }
-    return launch_preprocess_bwd(s, P, W, H, channels, means3D, scales, rotations, cov3D_precomp, opacities,
+    prof_mark(s, ST_BLEND_BWD);
+    const int rc_pre = launch_preprocess_bwd(s, P, W, H, channels, means3D, scales, rotations, cov3D_precomp, opacities,
                                  viewmatrix, projmatrix, scale_modifier, antialiasing != 0, radii, grad_scratch,
                                  dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales,
                                  dL_drotations, cam_sums);
+    prof_mark(s, ST_PREPROCESS_BWD);
+    return rc_pre;
 }
 
 EOGS_API int eogs_mark_visible(eogs_stream_t stream, int P, const float* means3D,

@@ -75,6 +75,16 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return eogs::cuda_fail(_e, name);    \
     } while (0)
 
+// ---- optional per-stage timing (instrumentation for bench.py; off by default) ----------------
+// When enabled on the calling thread, every stage boundary records a CUDA event on the launch
+// stream; eogs_profile_read() synchronises and returns the elapsed milliseconds per stage.
+enum Stage : int {
+    ST_BEGIN = 0, ST_PREPROCESS, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD,
+    ST_BWD_ZERO, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_COUNT
+};
+void prof_begin(cudaStream_t s);
+void prof_mark(cudaStream_t s, int stage);
+
 // ---- stage launchers (one per .cu) --------------------------------------------------------
 int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, int channels,
                           const float* means3D, const float* scales, const float* rotations,

@@ -165,6 +165,16 @@ EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channe
 EOGS_API int eogs_mark_visible(eogs_stream_t stream, int P, const float* means3D,
                       const float* viewmatrix, const float* projmatrix, uint8_t* present);
 
+/* ---- instrumentation ---------------------------------------------------------------- */
+/* Per-stage device times (CUDA events on the launch stream) of the calls made on this
+ * thread; off by default.  eogs_profile_read fills ms[stage] (milliseconds) for stage ids
+ * 1 preprocess, 2 depth sort, 3 scan, 4 emit, 5 tile sort, 6 ranges, 7 blend fwd,
+ * 8 bwd zeroing, 9 blend bwd, 10 preprocess bwd; it synchronises the recorded events and
+ * returns the number of stages recorded.  The forward render stage continues the timeline
+ * of the geometry stage, so the host sync between them is attributed to stage 4 (emit). */
+EOGS_API int eogs_profile_enable(int on);
+EOGS_API int eogs_profile_read(float* ms, int n);
+
 /* ---- inspection (parity tests) ----------------------------------------------------- */
 /* Copies internal state into caller buffers in the reference's layouts so that tests can
  * compare bit for bit.  Any output pointer may be NULL.

@@ -1,0 +1,456 @@
+/*
+ * eogs_oracle.c — CPU restatement (plain C, scalar) of the EOGS++ affine Gaussian rasterizer.
+ *
+ * TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load this.  The product
+ * (eogs2_b200/) never links, imports or executes anything under oracle/.
+ *
+ * What it restates (DGR = /root/reference/src/gaussiansplatting/submodules/diff-gaussian-rasterization):
+ *   oracle_preprocess   DGR/cuda_rasterizer/forward.cu:154-283 (preprocessCUDA), :117-151
+ *                       (computeCov3D), :74-112 (computeCov2D); auxiliary.h:40-78 (ndc2Pix,
+ *                       getRect, transformPoint4x3); cub InclusiveSum (rasterizer_impl.cu:280)
+ *   oracle_bin          rasterizer_impl.cu:70-111 (duplicateWithKeys), :306-311 (stable radix
+ *                       sort on tile|depth bits), :116-138 (identifyTileRanges)
+ *   oracle_blend_fwd    forward.cu:288-411 (renderCUDA)
+ *   oracle_blend_bwd    backward.cu:458-643 (renderCUDA backward)
+ *   oracle_pre_bwd      backward.cu:147-327 (computeCov2DCUDA), :400-454 (preprocessCUDA bwd),
+ *                       :331-394 (computeCov3D bwd); the dL_dT output uses the INTENDED stride
+ *                       6*idx+k (the reference writes idx+k, a data race, backward.cu:320-325)
+ *
+ * Bit-exactness: everything that feeds the sort keys and tile ranges (means2D, radius, rect,
+ * depth) is computed with the exact FMA/mul/add sequence that nvcc 12.9 emitted for the
+ * reference on sm_100a (read from its SASS; the same sequence is spelled with intrinsics in
+ * eogs2_b200/csrc/geom_math.cuh), using fmaf()/fma() and IEEE sqrt and division.  Compile with
+ * -ffp-contract=off so gcc adds no contractions of its own.  The blend uses libm expf, which
+ * differs from CUDA's expf by ulps, so images are compared with a tolerance (1e-4), not bit
+ * for bit.
+ *
+ * Pinning: tests/test_oracle_golden.py checks this file against tests/golden/ref_*.npz, which
+ * were produced by the compiled reference (oracle/_ref) on a B200 by tests/golden/make_golden.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define TILE 16
+#define NCH_MAX 5
+
+typedef struct { float t00, t01, t02, t10, t11, t12; } Affine2x3;
+
+static float f_bits(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static uint32_t u_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+/* a0*b0 + a1*b1 + a2*b2 as nvcc contracts it: middle product plain, then two FMAs */
+static float dot3_ref(float a0, float b0, float a1, float b1, float a2, float b2) {
+    return fmaf(a2, b2, fmaf(a0, b0, a1 * b1));
+}
+
+static Affine2x3 make_T(const float* v, int W, int H) {
+    const float hW = (float)((double)W * 0.5), hH = (float)((double)H * 0.5);
+    Affine2x3 T;
+    T.t00 = v[0] * hW; T.t01 = v[4] * hW; T.t02 = v[8] * hW;
+    T.t10 = v[1] * hH; T.t11 = v[5] * hH; T.t12 = v[9] * hH;
+    return T;
+}
+
+static float affine_row(const float* v, int k, float x, float y, float z) {
+    return fmaf(z, v[8 + k], fmaf(x, v[k], y * v[4 + k])) + v[12 + k];
+}
+
+/* R[c][r] column-major like glm; un-normalised quaternion (r,x,y,z) */
+static void quat_to_R(float r, float x, float y, float z, float R[3][3]) {
+    const float rx = r * x, xz = x * z, rz = r * z, yy = y * y, zz = z * z;
+    const float yz_m_rx = fmaf(y, z, -rx), yz_p_rx = fmaf(y, z, rx);
+    const float xz_p_ry = fmaf(r, y, xz), xz_m_ry = fmaf(-r, y, xz);
+    const float xx_p_yy = fmaf(x, x, yy), yy_p_zz = yy + zz, xx_p_zz = fmaf(x, x, zz);
+    const float xy_m_rz = fmaf(x, y, -rz), xy_p_rz = fmaf(x, y, rz);
+    R[0][0] = 1.f - (yy_p_zz + yy_p_zz); R[0][1] = xy_m_rz + xy_m_rz; R[0][2] = xz_p_ry + xz_p_ry;
+    R[1][0] = xy_p_rz + xy_p_rz; R[1][1] = 1.f - (xx_p_zz + xx_p_zz); R[1][2] = yz_m_rx + yz_m_rx;
+    R[2][0] = xz_m_ry + xz_m_ry; R[2][1] = yz_p_rx + yz_p_rx; R[2][2] = 1.f - (xx_p_yy + xx_p_yy);
+}
+
+static void cov3d_from_M(float M[3][3], float* c) {
+    c[0] = dot3_ref(M[0][0], M[0][0], M[0][1], M[0][1], M[0][2], M[0][2]);
+    c[1] = dot3_ref(M[1][0], M[0][0], M[1][1], M[0][1], M[1][2], M[0][2]);
+    c[2] = dot3_ref(M[2][0], M[0][0], M[2][1], M[0][1], M[2][2], M[0][2]);
+    c[3] = dot3_ref(M[1][0], M[1][0], M[1][1], M[1][1], M[1][2], M[1][2]);
+    c[4] = dot3_ref(M[2][0], M[1][0], M[2][1], M[1][1], M[2][2], M[1][2]);
+    c[5] = dot3_ref(M[2][0], M[2][0], M[2][1], M[2][1], M[2][2], M[2][2]);
+}
+
+static void scale_rot_M(const float* scale, float mod, const float* q, float R[3][3], float M[3][3], float s[3]) {
+    quat_to_R(q[0], q[1], q[2], q[3], R);
+    for (int k = 0; k < 3; k++) s[k] = mod * scale[k];
+    for (int c = 0; c < 3; c++)
+        for (int k = 0; k < 3; k++) M[c][k] = s[k] * R[c][k];
+}
+
+static void cov2d(const Affine2x3* T, const float* c, float* xx, float* xy, float* yy) {
+    const float X00 = dot3_ref(T->t00, c[0], T->t01, c[1], T->t02, c[2]);
+    const float X01 = dot3_ref(T->t10, c[0], T->t11, c[1], T->t12, c[2]);
+    const float X10 = dot3_ref(T->t00, c[1], T->t01, c[3], T->t02, c[4]);
+    const float X11 = dot3_ref(T->t10, c[1], T->t11, c[3], T->t12, c[4]);
+    const float X20 = dot3_ref(T->t00, c[2], T->t01, c[4], T->t02, c[5]);
+    const float X21 = dot3_ref(T->t10, c[2], T->t11, c[4], T->t12, c[5]);
+    *xx = dot3_ref(X00, T->t00, X10, T->t01, X20, T->t02);
+    *xy = dot3_ref(X01, T->t00, X11, T->t01, X21, T->t02);
+    *yy = dot3_ref(X01, T->t10, X11, T->t11, X21, T->t12);
+}
+
+static float ndc_to_pix(float v, int S) { return (float)(fma((double)v + 1.0, (double)S, -1.0) * 0.5); }
+
+static int f2i_trunc_clamped(float f) {          /* CUDA cvt.rzi saturates; C would be UB */
+    if (!(f == f)) return 0;
+    if (f >= 2147483520.f) return 2147483647;
+    if (f <= -2147483648.f) return (-2147483647 - 1);
+    return (int)f;
+}
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+static void get_rect(float px, float py, int radius, int gx, int gy, int* x0, int* y0, int* x1, int* y1) {
+    const float rf = (float)radius;
+    *x0 = imin(gx, imax(0, f2i_trunc_clamped((px - rf) * 0.0625f)));
+    *y0 = imin(gy, imax(0, f2i_trunc_clamped((py - rf) * 0.0625f)));
+    *x1 = imin(gx, imax(0, f2i_trunc_clamped((((px + rf) + 16.f) - 1.f) * 0.0625f)));
+    *y1 = imin(gy, imax(0, f2i_trunc_clamped((((py + rf) + 16.f) - 1.f) * 0.0625f)));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * preprocess: returns num_rendered (sum of tiles_touched), or -1 when an altitude exceeds 200
+ * (the reference traps).  Outputs for culled Gaussians: radii = tiles_touched = 0, others 0.
+ * ---------------------------------------------------------------------------------------- */
+long long oracle_preprocess(int P, int W, int H, const float* means3D, const float* scales,
+                            const float* rotations, const float* cov3D_precomp, const float* opacities,
+                            const float* view, float scale_modifier, int antialiasing,
+                            int32_t* radii, float* means2D, float* depths, float* conic_opacity,
+                            float* cov3D, uint32_t* tiles_touched)
+{
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    const Affine2x3 T = make_T(view, W, H);
+    long long total = 0;
+    int too_high = 0;
+    for (int i = 0; i < P; i++) {
+        radii[i] = 0; tiles_touched[i] = 0;
+        means2D[2 * i] = means2D[2 * i + 1] = 0.f; depths[i] = 0.f;
+        for (int k = 0; k < 4; k++) conic_opacity[4 * i + k] = 0.f;
+        const float x = means3D[3 * i], y = means3D[3 * i + 1], z = means3D[3 * i + 2];
+        const float tx = affine_row(view, 0, x, y, z), ty = affine_row(view, 1, x, y, z), tz = affine_row(view, 2, x, y, z);
+        float c3[6];
+        if (cov3D_precomp) memcpy(c3, cov3D_precomp + 6 * (size_t)i, sizeof(c3));
+        else {
+            float R[3][3], M[3][3], s[3];
+            scale_rot_M(scales + 3 * (size_t)i, scale_modifier, rotations + 4 * (size_t)i, R, M, s);
+            cov3d_from_M(M, c3);
+        }
+        if (cov3D) memcpy(cov3D + 6 * (size_t)i, c3, sizeof(c3));
+        float cxx, cxy, cyy;
+        cov2d(&T, c3, &cxx, &cxy, &cyy);
+        const float b2 = cxy * cxy;
+        const float det_cov = fmaf(cxx, cyy, -b2);
+        const float a = cxx + 0.3f, c = cyy + 0.3f;
+        const float det = fmaf(a, c, -b2);
+        float aa_scale = 1.0f;
+        if (antialiasing) aa_scale = sqrtf(fmaxf(0.000025f, det_cov / det));
+        if (det == 0.0f) continue;
+        const float det_inv = 1.f / det;
+        const float mid = (a + c) * 0.5f;
+        const float root = sqrtf(fmaxf(0.1f, fmaf(mid, mid, -det)));
+        const float lam = fmaxf(mid + root, mid - root);
+        const int radius = (int)ceilf(sqrtf(lam) * 3.f);
+        const float px = ndc_to_pix(tx, W), py = ndc_to_pix(ty, H);
+        int x0, y0, x1, y1;
+        get_rect(px, py, radius, gx, gy, &x0, &y0, &x1, &y1);
+        const uint32_t area = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+        if (area == 0) continue;
+        const float d = 200.0f - tz;
+        if (d < 0.f) { too_high = 1; continue; }
+        depths[i] = d;
+        radii[i] = radius;
+        means2D[2 * i] = px; means2D[2 * i + 1] = py;
+        conic_opacity[4 * i] = c * det_inv;
+        conic_opacity[4 * i + 1] = (-cxy) * det_inv;
+        conic_opacity[4 * i + 2] = a * det_inv;
+        conic_opacity[4 * i + 3] = opacities[i] * aa_scale;
+        tiles_touched[i] = area;
+        total += area;
+    }
+    return too_high ? -1 : total;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * binning: keys = (tile << 32) | depth bits, emitted idx-ascending then row-major over the rect;
+ * stable sort == sort by (key, emission index); ranges like identifyTileRanges.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { uint64_t key; uint32_t val; uint32_t seq; } KV;
+static int kv_cmp(const void* a, const void* b) {
+    const KV* x = (const KV*)a; const KV* y = (const KV*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->seq < y->seq ? -1 : (x->seq > y->seq);
+}
+
+int oracle_bin(int P, int W, int H, long long num_rendered, const int32_t* radii, const float* means2D,
+               const float* depths, uint64_t* keys_sorted, uint32_t* point_list, uint32_t* ranges /*[tiles*2]*/)
+{
+    const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+    memset(ranges, 0, sizeof(uint32_t) * 2 * (size_t)gx * gy);
+    if (num_rendered == 0) return 0;
+    KV* kv = (KV*)malloc(sizeof(KV) * (size_t)num_rendered);
+    if (!kv) return -1;
+    size_t off = 0;
+    for (int i = 0; i < P; i++) {
+        if (radii[i] <= 0) continue;
+        int x0, y0, x1, y1;
+        get_rect(means2D[2 * i], means2D[2 * i + 1], radii[i], gx, gy, &x0, &y0, &x1, &y1);
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) {
+                kv[off].key = ((uint64_t)((uint32_t)(y * gx + x)) << 32) | u_bits(depths[i]);
+                kv[off].val = (uint32_t)i;
+                kv[off].seq = (uint32_t)off;
+                off++;
+            }
+    }
+    if ((long long)off != num_rendered) { free(kv); return -2; }
+    qsort(kv, off, sizeof(KV), kv_cmp);
+    for (size_t j = 0; j < off; j++) {
+        keys_sorted[j] = kv[j].key; point_list[j] = kv[j].val;
+        const uint32_t cur = (uint32_t)(kv[j].key >> 32);
+        if (j == 0) ranges[2 * cur] = 0;
+        else {
+            const uint32_t prev = (uint32_t)(kv[j - 1].key >> 32);
+            if (cur != prev) { ranges[2 * prev + 1] = (uint32_t)j; ranges[2 * cur] = (uint32_t)j; }
+        }
+        if (j == off - 1) ranges[2 * cur + 1] = (uint32_t)off;
+    }
+    free(kv);
+    return 0;
+}
+
+/* power and alpha exactly as the reference's SASS orders them (forward.cu:361-372) */
+static float pair_power(float mx, float my, float cx, float cy, float cz, float pxf, float pyf, float* dx, float* dy) {
+    *dx = mx - pxf; *dy = my - pyf;
+    const float quad = fmaf(*dx, cx * *dx, (cz * *dy) * *dy);
+    return fmaf(quad, -0.5f, -((cy * *dx) * *dy));
+}
+
+/* ------------------------------------------------------------------------------------------
+ * forward blend (forward.cu:288-411)
+ * ---------------------------------------------------------------------------------------- */
+void oracle_blend_fwd(int W, int H, int C, const uint32_t* ranges, const uint32_t* point_list,
+                      const float* means2D, const float* conic_opacity, const float* colors,
+                      const float* depths, const float* bg, float* out_color, float* out_invdepth,
+                      float* final_T, uint32_t* n_contrib)
+{
+    const int gx = (W + TILE - 1) / TILE;
+    for (int py = 0; py < H; py++)
+        for (int px = 0; px < W; px++) {
+            const uint32_t tile = (uint32_t)((py / TILE) * gx + px / TILE);
+            const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
+            const float pxf = (float)px, pyf = (float)py;
+            float T = 1.0f, acc[NCH_MAX] = {0, 0, 0, 0, 0}, accd = 0.f;
+            uint32_t contributor = 0, last = 0;
+            for (uint32_t j = r0; j < r1; j++) {
+                contributor++;
+                const uint32_t id = point_list[j];
+                const float* co = conic_opacity + 4 * (size_t)id;
+                float dx, dy;
+                const float power = pair_power(means2D[2 * id], means2D[2 * id + 1], co[0], co[1], co[2], pxf, pyf, &dx, &dy);
+                if (power > 0.0f) continue;
+                const float alpha = fminf(0.99f, co[3] * expf(power));
+                if (alpha < 1.0f / 255.0f) continue;
+                const float test_T = T * (1.f - alpha);
+                if (test_T < 0.0001f) break;
+                for (int ch = 0; ch < C; ch++) acc[ch] = fmaf(T, alpha * colors[(size_t)id * C + ch], acc[ch]);
+                accd = fmaf(T, alpha * (1.f / depths[id]), accd);
+                T = test_T;
+                last = contributor;
+            }
+            const size_t pid = (size_t)py * W + px;
+            final_T[pid] = T;
+            n_contrib[pid] = last;
+            for (int ch = 0; ch < C; ch++) out_color[(size_t)ch * H * W + pid] = fmaf(bg[ch], T, acc[ch]);
+            if (out_invdepth) out_invdepth[pid] = accd;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * backward blend (backward.cu:458-643): per pixel back to front; per-Gaussian sums in double.
+ * dL_dconic is [P,4] with (.x, .y, unused, .w) like the reference's float4.
+ * ---------------------------------------------------------------------------------------- */
+void oracle_blend_bwd(int P, int W, int H, int C, const uint32_t* ranges, const uint32_t* point_list,
+                      const float* means2D, const float* conic_opacity, const float* colors,
+                      const float* depths, const float* bg, const float* final_T, const uint32_t* n_contrib,
+                      const float* dL_dpix, const float* dL_dinvdepth_pix,
+                      double* dL_dmean2D /*[P,2]*/, double* dL_dconic /*[P,4]*/, double* dL_dopacity /*[P]*/,
+                      double* dL_dcolors /*[P,C]*/, double* dL_dinvdepths /*[P]*/)
+{
+    const int gx = (W + TILE - 1) / TILE;
+    memset(dL_dmean2D, 0, sizeof(double) * 2 * (size_t)P);
+    memset(dL_dconic, 0, sizeof(double) * 4 * (size_t)P);
+    memset(dL_dopacity, 0, sizeof(double) * (size_t)P);
+    memset(dL_dcolors, 0, sizeof(double) * (size_t)C * P);
+    memset(dL_dinvdepths, 0, sizeof(double) * (size_t)P);
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    for (int py = 0; py < H; py++)
+        for (int px = 0; px < W; px++) {
+            const uint32_t tile = (uint32_t)((py / TILE) * gx + px / TILE);
+            const uint32_t r0 = ranges[2 * tile];
+            const size_t pid = (size_t)py * W + px;
+            const float pxf = (float)px, pyf = (float)py;
+            const float T_final = final_T[pid];
+            float T = T_final;
+            float g[NCH_MAX], accum_rec[NCH_MAX] = {0, 0, 0, 0, 0}, last_color[NCH_MAX] = {0, 0, 0, 0, 0};
+            for (int ch = 0; ch < C; ch++) g[ch] = dL_dpix[(size_t)ch * H * W + pid];
+            const float g_inv = dL_dinvdepth_pix ? dL_dinvdepth_pix[pid] : 0.f;
+            float last_alpha = 0.f, accum_inv = 0.f, last_inv = 0.f;
+            float bg_dot = 0.f;
+            for (int ch = 0; ch < C; ch++) bg_dot += bg[ch] * g[ch];
+            for (int k = (int)n_contrib[pid] - 1; k >= 0; k--) {
+                const uint32_t id = point_list[r0 + (uint32_t)k];
+                const float* co = conic_opacity + 4 * (size_t)id;
+                float dx, dy;
+                const float power = pair_power(means2D[2 * id], means2D[2 * id + 1], co[0], co[1], co[2], pxf, pyf, &dx, &dy);
+                if (power > 0.0f) continue;
+                const float G = expf(power);
+                const float alpha = fminf(0.99f, co[3] * G);
+                if (alpha < 1.0f / 255.0f) continue;
+                T = T / (1.f - alpha);
+                const float dchannel_dcolor = alpha * T;
+                float dL_dalpha = 0.f;
+                for (int ch = 0; ch < C; ch++) {
+                    const float c = colors[(size_t)id * C + ch];
+                    accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
+                    last_color[ch] = c;
+                    dL_dalpha += (c - accum_rec[ch]) * g[ch];
+                    dL_dcolors[(size_t)id * C + ch] += (double)(dchannel_dcolor * g[ch]);
+                }
+                if (dL_dinvdepth_pix) {
+                    const float invd = 1.f / depths[id];
+                    accum_inv = last_alpha * last_inv + (1.f - last_alpha) * accum_inv;
+                    last_inv = invd;
+                    dL_dalpha += (invd - accum_inv) * g_inv;
+                    dL_dinvdepths[id] += (double)(dchannel_dcolor * g_inv);
+                }
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                const float dL_dG = co[3] * dL_dalpha;
+                const float gdx = G * dx, gdy = G * dy;
+                const float dG_ddelx = -gdx * co[0] - gdy * co[1];
+                const float dG_ddely = -gdy * co[2] - gdx * co[1];
+                dL_dmean2D[2 * (size_t)id] += (double)(dL_dG * dG_ddelx * ddelx_dx);
+                dL_dmean2D[2 * (size_t)id + 1] += (double)(dL_dG * dG_ddely * ddely_dy);
+                dL_dconic[4 * (size_t)id] += (double)(-0.5f * gdx * dx * dL_dG);
+                dL_dconic[4 * (size_t)id + 1] += (double)(-0.5f * gdx * dy * dL_dG);
+                dL_dconic[4 * (size_t)id + 3] += (double)(-0.5f * gdy * dy * dL_dG);
+                dL_dopacity[id] += (double)(G * dL_dalpha);
+            }
+        }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * preprocess backward (backward.cu:147-327, :331-394, :400-454).  Inputs are the float
+ * per-Gaussian sums of the blend backward.  dL_dT is [P,6] with the intended stride.
+ * ---------------------------------------------------------------------------------------- */
+void oracle_pre_bwd(int P, int W, int H, const float* means3D, const float* scales, const float* rotations,
+                    const float* cov3D_precomp, const float* opacities, const float* view, const float* proj,
+                    float scale_modifier, int antialiasing, const int32_t* radii,
+                    const float* dL_dmean2D /*[P,2]*/, const float* dL_dconic /*[P,4]*/, float* dL_dopacity /*[P] in/out*/,
+                    float* dL_dmean3D /*[P,3]*/, float* dL_dcov3D /*[P,6]*/, float* dL_dscale /*[P,3]*/,
+                    float* dL_drot /*[P,4]*/, float* dL_dT /*[P,6]*/)
+{
+    const Affine2x3 T = make_T(view, W, H);
+    const float h_var = 0.3f;
+    for (int i = 0; i < P; i++) {
+        for (int k = 0; k < 3; k++) dL_dmean3D[3 * (size_t)i + k] = 0.f;
+        for (int k = 0; k < 6; k++) { dL_dcov3D[6 * (size_t)i + k] = 0.f; dL_dT[6 * (size_t)i + k] = 0.f; }
+        if (dL_dscale) for (int k = 0; k < 3; k++) dL_dscale[3 * (size_t)i + k] = 0.f;
+        if (dL_drot) for (int k = 0; k < 4; k++) dL_drot[4 * (size_t)i + k] = 0.f;
+        if (!(radii[i] > 0)) continue;
+        float c3[6], R[3][3], M[3][3], s[3];
+        if (cov3D_precomp) memcpy(c3, cov3D_precomp + 6 * (size_t)i, sizeof(c3));
+        else {
+            scale_rot_M(scales + 3 * (size_t)i, scale_modifier, rotations + 4 * (size_t)i, R, M, s);
+            cov3d_from_M(M, c3);
+        }
+        float c_xx, c_xy, c_yy;
+        cov2d(&T, c3, &c_xx, &c_xy, &c_yy);
+        const float dcx = dL_dconic[4 * (size_t)i], dcy = dL_dconic[4 * (size_t)i + 1], dcw = dL_dconic[4 * (size_t)i + 3];
+        float dxx = 0.f, dxy = 0.f, dyy = 0.f;
+        if (antialiasing) {
+            const float det_cov = c_xx * c_yy - c_xy * c_xy;
+            c_xx += h_var; c_yy += h_var;
+            const float det_plus = c_xx * c_yy - c_xy * c_xy;
+            const float ratio = det_cov / det_plus;
+            const float hs = sqrtf(fmaxf(0.000025f, ratio));
+            const float v = dL_dopacity[i];
+            const float d_h = v * opacities[i];
+            dL_dopacity[i] = v * hs;
+            const float d_inside_root = ratio <= 0.000025f ? 0.f : d_h / (2 * hs);
+            const float x = c_xx, y = c_yy, z = c_xy, w = h_var;
+            const float den = w * w + w * (x + y) + x * y - z * z;
+            const float denom_f = d_inside_root / (den * den);
+            dxx = w * (w * y + y * y + z * z) * denom_f;
+            dyy = w * (w * x + x * x + z * z) * denom_f;
+            dxy = -2.f * w * z * (w + x + y) * denom_f;
+        } else { c_xx += h_var; c_yy += h_var; }
+        const float denom = c_xx * c_yy - c_xy * c_xy;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        float* gc = dL_dcov3D + 6 * (size_t)i;
+        if (denom2inv != 0) {
+            dxx += denom2inv * (-c_yy * c_yy * dcx + 2 * c_xy * c_yy * dcy + (denom - c_xx * c_yy) * dcw);
+            dyy += denom2inv * (-c_xx * c_xx * dcw + 2 * c_xx * c_xy * dcy + (denom - c_xx * c_yy) * dcx);
+            dxy += denom2inv * 2 * (c_xy * c_yy * dcx - (denom + 2 * c_xy * c_xy) * dcy + c_xx * c_xy * dcw);
+            gc[0] = T.t00 * T.t00 * dxx + T.t00 * T.t10 * dxy + T.t10 * T.t10 * dyy;
+            gc[3] = T.t01 * T.t01 * dxx + T.t01 * T.t11 * dxy + T.t11 * T.t11 * dyy;
+            gc[5] = T.t02 * T.t02 * dxx + T.t02 * T.t12 * dxy + T.t12 * T.t12 * dyy;
+            gc[1] = 2 * T.t00 * T.t01 * dxx + (T.t00 * T.t11 + T.t01 * T.t10) * dxy + 2 * T.t10 * T.t11 * dyy;
+            gc[2] = 2 * T.t00 * T.t02 * dxx + (T.t00 * T.t12 + T.t02 * T.t10) * dxy + 2 * T.t10 * T.t12 * dyy;
+            gc[4] = 2 * T.t02 * T.t01 * dxx + (T.t01 * T.t12 + T.t02 * T.t11) * dxy + 2 * T.t11 * T.t12 * dyy;
+        }
+        const float tv0 = T.t00 * c3[0] + T.t01 * c3[1] + T.t02 * c3[2];
+        const float tv1 = T.t00 * c3[1] + T.t01 * c3[3] + T.t02 * c3[4];
+        const float tv2 = T.t00 * c3[2] + T.t01 * c3[4] + T.t02 * c3[5];
+        const float uv0 = T.t10 * c3[0] + T.t11 * c3[1] + T.t12 * c3[2];
+        const float uv1 = T.t10 * c3[1] + T.t11 * c3[3] + T.t12 * c3[4];
+        const float uv2 = T.t10 * c3[2] + T.t11 * c3[4] + T.t12 * c3[5];
+        float* gT = dL_dT + 6 * (size_t)i;
+        gT[0] = 2 * tv0 * dxx + uv0 * dxy; gT[1] = 2 * tv1 * dxx + uv1 * dxy; gT[2] = 2 * tv2 * dxx + uv2 * dxy;
+        gT[3] = 2 * uv0 * dyy + tv0 * dxy; gT[4] = 2 * uv1 * dyy + tv1 * dxy; gT[5] = 2 * uv2 * dyy + tv2 * dxy;
+
+        const float gxm = dL_dmean2D[2 * (size_t)i], gym = dL_dmean2D[2 * (size_t)i + 1];
+        dL_dmean3D[3 * (size_t)i] = proj[0] * gxm + proj[1] * gym;
+        dL_dmean3D[3 * (size_t)i + 1] = proj[4] * gxm + proj[5] * gym;
+        dL_dmean3D[3 * (size_t)i + 2] = proj[8] * gxm + proj[9] * gym;
+
+        if (!cov3D_precomp && dL_dscale && dL_drot) {
+            const float dS[3][3] = {{gc[0], 0.5f * gc[1], 0.5f * gc[2]}, {0.5f * gc[1], gc[3], 0.5f * gc[4]},
+                                    {0.5f * gc[2], 0.5f * gc[4], gc[5]}};
+            float D[3][3];
+            for (int k = 0; k < 3; k++) {
+                float gs = 0.f;
+                for (int c = 0; c < 3; c++) {
+                    const float dM = 2.f * (M[0][k] * dS[c][0] + M[1][k] * dS[c][1] + M[2][k] * dS[c][2]);
+                    gs += R[c][k] * dM;
+                    D[k][c] = s[k] * dM;
+                }
+                dL_dscale[3 * (size_t)i + k] = gs;
+            }
+            const float* q = rotations + 4 * (size_t)i;
+            const float r = q[0], x = q[1], y = q[2], z = q[3];
+            float* gq = dL_drot + 4 * (size_t)i;
+            gq[0] = 2 * z * (D[0][1] - D[1][0]) + 2 * y * (D[2][0] - D[0][2]) + 2 * x * (D[1][2] - D[2][1]);
+            gq[1] = 2 * y * (D[1][0] + D[0][1]) + 2 * z * (D[2][0] + D[0][2]) + 2 * r * (D[1][2] - D[2][1]) - 4 * x * (D[2][2] + D[1][1]);
+            gq[2] = 2 * x * (D[1][0] + D[0][1]) + 2 * r * (D[2][0] - D[0][2]) + 2 * z * (D[1][2] + D[2][1]) - 4 * y * (D[2][2] + D[0][0]);
+            gq[3] = 2 * r * (D[0][1] - D[1][0]) + 2 * x * (D[2][0] + D[0][2]) + 2 * y * (D[1][2] + D[2][1]) - 4 * z * (D[1][1] + D[0][0]);
+        }
+    }
+}
+
+uint32_t oracle_higher_msb(uint32_t n) {        /* getHigherMsb, rasterizer_impl.cu:35-50 */
+    uint32_t msb = sizeof(n) * 4, step = msb;
+    while (step > 1) { step /= 2; if (n >> msb) msb += step; else msb -= step; }
+    if (n >> msb) msb++;
+    return msb;
+}

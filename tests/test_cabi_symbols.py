@@ -1,0 +1,64 @@
+"""CPU: the C-ABI library loads and exports every symbol include/eogs_raster.h declares; host-only
+size queries behave; the Python surface has the reference's names and field order."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "eogs_raster.h"
+
+
+def declared_symbols():
+    text = HEADER.read_text()
+    return sorted(set(re.findall(r"EOGS_API\s+[\w\s\*]+?\b(eogs_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_boundary():
+    names = declared_symbols()
+    for must in ("eogs_forward_geometry", "eogs_forward_render", "eogs_rasterize_forward", "eogs_backward",
+                 "eogs_mark_visible", "eogs_export_state", "eogs_geom_bytes", "eogs_image_bytes",
+                 "eogs_binning_bytes", "eogs_last_error", "eogs_abi_version"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from eogs2_b200 import _cabi, build
+    build.build()
+    lib = ctypes.CDLL(str(_cabi.LIB_PATH))
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    # and the ctypes table covers the header one to one
+    assert sorted(_cabi.SIGNATURES) == declared_symbols()
+
+
+def test_only_the_c_abi_is_exported():
+    from eogs2_b200 import _cabi
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_cabi.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = [ln.split()[-1] for ln in out.splitlines() if " T " in ln]
+    assert exported and all(s.startswith("eogs_") for s in exported), exported
+
+
+def test_size_queries_are_host_only_and_monotonic():
+    from eogs2_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.eogs_abi_version() == 1
+    g1, g2 = lib.eogs_geom_bytes(1000), lib.eogs_geom_bytes(1_000_000)
+    assert 0 < g1 < g2 and g2 >= 1_000_000 * (48 + 4 + 8 + 4 * 6)
+    assert lib.eogs_image_bytes(2048, 2048) >= 2048 * 2048 * 8 + 16384 * 8
+    assert lib.eogs_binning_bytes(2048, 2048, 10_000_000) >= 10_000_000 * 12
+    assert lib.eogs_geom_bytes(0) > 0
+
+
+def test_python_surface_matches_reference_names():
+    import diff_gaussian_rasterization as d
+    assert d.GaussianRasterizationSettings._fields == (
+        "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+        "sh_degree", "campos", "prefiltered", "debug", "antialiasing")     # DGR __init__.py:219-232
+    import inspect
+    sig = inspect.signature(d.GaussianRasterizer.forward)
+    assert list(sig.parameters) == ["self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                    "rotations", "cov3D_precomp"]          # DGR __init__.py:250-260
+    assert hasattr(d.GaussianRasterizer, "markVisible") and callable(d.rasterize_gaussians)
