@@ -186,7 +186,8 @@ def render_fwd_bwd(scene_tensors, view, bg, W, H, dL_dcolor, dL_dinvdepth=None, 
     loss = (out * dL_dcolor).sum()
     if dL_dinvdepth is not None:
         loss = loss + (outd * dL_dinvdepth).sum()
-    loss.backward()
+    if loss.requires_grad:        # an empty tile window blends nothing
+        loss.backward()
     geo = aux["geo"]
     return dict(color=out.detach(), invdepth=outd.detach(), radii=radii, aux=aux,
                 dL_dmeans3D=means3D.grad, dL_dscales=scales.grad, dL_drotations=rotations.grad,
