@@ -17,7 +17,8 @@
 //     into one scalar recurrence on the dot product with dL_dpixel (same linear map);
 //   - dL_dinvdepth per Gaussian is not accumulated: the reference computes it and drops it
 //     (backward.cu:305-307 commented out; it never reaches a returned gradient);
-//   - packed 48-byte records gathered with cp.async, double-buffered (see blend_fwd.cu).
+//   - exact tile culling + warp-segment compaction at staging time and a register-prefetch
+//     pipeline with one barrier per batch, exactly as in blend_fwd.cu.
 //
 // Bound: FP32 issue + shuffle + L2 reduction throughput.  Algorithmic HBM bytes: 52 B gathered +
 // <= 8 warps x 44 B reduced per instance, 4*(C+1) + 8 B per pixel in.
@@ -78,17 +79,22 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  float* __restrict__ grad_rec)
 {
     constexpr int NV = 6 + C;   // mean2D.xy, conic.xyw, opacity, colours
+    constexpr int NWARPS = BWD_THREADS / 32;
     __shared__ float4 s_rec[2][REC_F4][BWD_THREADS];
     __shared__ uint32_t s_id[2][BWD_THREADS];
+    __shared__ uint16_t s_pos[2][BWD_THREADS];
+    __shared__ int s_cnt[2][NWARPS];
     __shared__ int s_nmax;
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint32_t lx, ly;
     tile_pixel(tid, lx, ly);
     const uint32_t pix_x = blockIdx.x * TILE + lx, pix_y = blockIdx.y * TILE + ly;
     const bool inside = pix_x < (uint32_t)W && pix_y < (uint32_t)H;
     const size_t pix_id = (size_t)pix_y * W + pix_x;
     const float pixfx = (float)pix_x, pixfy = (float)pix_y;
+    const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);
+    const float tx1 = fminf(tx0 + (TILE - 1), (float)(W - 1)), ty1 = fminf(ty0 + (TILE - 1), (float)(H - 1));
 
     const uint2 range = __ldg(ranges + blockIdx.y * gridDim.x + blockIdx.x);
     const uint32_t* list = point_list + range.x;
@@ -103,18 +109,35 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     if (nmax == 0) return;
     const int rounds = (nmax + BWD_THREADS - 1) / BWD_THREADS;
 
-    auto gather = [&](int stage, int batch) {
-        const int p = nmax - 1 - (batch * BWD_THREADS + (int)tid);   // back to front
-        if (p >= 0) {
-            const uint32_t id = __ldg(list + p);
-            s_id[stage][tid] = id;
-            const float4* src = splat + (size_t)id * REC_F4;
-#pragma unroll
-            for (int k = 0; k < REC_F4; k++) cp_async16(&s_rec[stage][k][tid], src + k);
-        }
+    // Batch b, thread t holds list position nmax-1 - (b*256 + t): back to front.
+    auto list_pos = [&](int batch) { return nmax - 1 - (batch * BWD_THREADS + (int)tid); };
+    auto fetch = [&](uint32_t id, float4& r0, float4& r1, float4& r2) {
+        const float4* src = splat + (size_t)id * REC_F4;
+        r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2);
     };
-    gather(0, 0);
-    cp_async_commit();
+    // cull + compact (same exact tile test as the forward, so the same entries survive)
+    auto stage_write = [&](int stage, bool have, uint32_t id, const float4& r0, const float4& r1, const float4& r2) {
+        const bool keep = have && tile_may_contribute(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0, tx1, ty1);
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const uint32_t slot = warp * 32u + __popc(ballot & ((1u << lane) - 1u));
+            s_rec[stage][0][slot] = r0;
+            s_rec[stage][1][slot] = r1;
+            s_rec[stage][2][slot] = r2;
+            s_id[stage][slot] = id;
+            s_pos[stage][slot] = (uint16_t)tid;
+        }
+        if (lane == 0) s_cnt[stage][warp] = __popc(ballot);
+    };
+
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    uint32_t rid = 0, id_next = 0;
+    {   // prologue: batch 0 staged, ids of batch 1 in registers
+        const bool have = list_pos(0) >= 0;
+        if (have) { rid = __ldg(list + list_pos(0)); fetch(rid, r0, r1, r2); }
+        if (list_pos(1) >= 0) id_next = __ldg(list + list_pos(1));
+        stage_write(0, have, rid, r0, r1, r2);
+    }
 
     const float T_final = inside ? __ldg(final_T + pix_id) : 0.f;
     float T = T_final;
@@ -132,64 +155,68 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int my_slot = fold_slot<NV>(lane);
 
     for (int i = 0; i < rounds; i++) {
-        cp_async_wait<0>();
-        __syncthreads();
-        if (i + 1 < rounds) gather((i + 1) & 1, i + 1);
-        cp_async_commit();
+        __syncthreads();                 // stage i&1 complete; the other stage is free again
+        const bool more = i + 1 < rounds;
+        const bool have_next = more && list_pos(i + 1) >= 0;
+        if (have_next) { rid = id_next; fetch(rid, r0, r1, r2); }  // in flight during the replay below
+        if (list_pos(i + 2) >= 0) id_next = __ldg(list + list_pos(i + 2));
 
         const int stage = i & 1;
-        const int first = nmax - 1 - i * BWD_THREADS;          // list position of entry j = 0
-        const int cnt = min(BWD_THREADS, first + 1);
-        for (int j = 0; j < cnt; j++) {
-            // Entry at list position p is blended by this pixel iff p < n_contrib (backward.cu:556-558).
-            const bool active = (first - j) < last_contributor;
-            const float4 ra = s_rec[stage][0][j];
-            const float4 rb = s_rec[stage][1][j];
-            const float dx = __fsub_rn(ra.x, pixfx), dy = __fsub_rn(ra.y, pixfy);
-            const float quad = __fmaf_rn(dx, __fmul_rn(ra.z, dx), __fmul_rn(__fmul_rn(rb.x, dy), dy));
-            const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx), dy));
-            const float G = expf(power);
-            const float alpha = fminf(0.99f, __fmul_rn(rb.y, G));
-            const bool valid = active && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (!__any_sync(0xffffffffu, valid)) continue;
+        const int first = nmax - 1 - i * BWD_THREADS;              // list position of batch slot 0
+        for (int seg = 0; seg < NWARPS; seg++) {
+            const int cnt = s_cnt[stage][seg];
+            const int base = seg * 32;
+            for (int j = base; j < base + cnt; j++) {
+                // Entry at list position p is blended by this pixel iff p < n_contrib (backward.cu:556-558).
+                const bool active = (first - (int)s_pos[stage][j]) < last_contributor;
+                const float4 ra = s_rec[stage][0][j];
+                const float4 rb = s_rec[stage][1][j];
+                const float dx = __fsub_rn(ra.x, pixfx), dy = __fsub_rn(ra.y, pixfy);
+                const float quad = __fmaf_rn(dx, __fmul_rn(ra.z, dx), __fmul_rn(__fmul_rn(rb.x, dy), dy));
+                const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx), dy));
+                const float G = expf(power);
+                const float alpha = fminf(0.99f, __fmul_rn(rb.y, G));
+                const bool valid = active && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                if (!__any_sync(0xffffffffu, valid)) continue;
 
-            float v[NV];
+                float v[NV];
 #pragma unroll
-            for (int k = 0; k < NV; k++) v[k] = 0.f;
-            if (valid) {
-                const float4 rc = s_rec[stage][2][j];
-                const float col[5] = {rb.z, rb.w, rc.x, rc.y, rc.z};
-                const float inv_1ma = __fdividef(1.f, 1.f - alpha);
-                T *= inv_1ma;
-                const float w = alpha * T;
-                float cg = rc.w * g_inv;
+                for (int k = 0; k < NV; k++) v[k] = 0.f;
+                if (valid) {
+                    const float4 rc = s_rec[stage][2][j];
+                    const float col[5] = {rb.z, rb.w, rc.x, rc.y, rc.z};
+                    const float inv_1ma = __fdividef(1.f, 1.f - alpha);
+                    T *= inv_1ma;
+                    const float w = alpha * T;
+                    float cg = rc.w * g_inv;
 #pragma unroll
-                for (int ch = 0; ch < C; ch++) {
-                    v[6 + ch] = w * g[ch];
-                    cg = fmaf(col[ch], g[ch], cg);
+                    for (int ch = 0; ch < C; ch++) {
+                        v[6 + ch] = w * g[ch];
+                        cg = fmaf(col[ch], g[ch], cg);
+                    }
+                    accum_rec = fmaf(last_alpha, last_cg, (1.f - last_alpha) * accum_rec);
+                    last_cg = cg;
+                    last_alpha = alpha;
+                    float dL_dalpha = (cg - accum_rec) * T;
+                    dL_dalpha = fmaf(-T_final * inv_1ma, bg_dot_g, dL_dalpha);
+
+                    const float dL_dG = rb.y * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
+                    const float dG_ddely = -gdy * rb.x - gdx * ra.w;
+                    v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                    v[1] = dL_dG * dG_ddely * ddely_dy;
+                    v[2] = -0.5f * gdx * dx * dL_dG;
+                    v[3] = -0.5f * gdx * dy * dL_dG;
+                    v[4] = -0.5f * gdy * dy * dL_dG;
+                    v[5] = G * dL_dalpha;
                 }
-                accum_rec = fmaf(last_alpha, last_cg, (1.f - last_alpha) * accum_rec);
-                last_cg = cg;
-                last_alpha = alpha;
-                float dL_dalpha = (cg - accum_rec) * T;
-                dL_dalpha = fmaf(-T_final * inv_1ma, bg_dot_g, dL_dalpha);
-
-                const float dL_dG = rb.y * dL_dalpha;
-                const float gdx = G * dx, gdy = G * dy;
-                const float dG_ddelx = -gdx * ra.z - gdy * ra.w;
-                const float dG_ddely = -gdy * rb.x - gdx * ra.w;
-                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                v[1] = dL_dG * dG_ddely * ddely_dy;
-                v[2] = -0.5f * gdx * dx * dL_dG;
-                v[3] = -0.5f * gdx * dy * dL_dG;
-                v[4] = -0.5f * gdy * dy * dL_dG;
-                v[5] = G * dL_dalpha;
+                warp_transpose_reduce<NV>(v, lane);
+                if (my_slot >= 0) atomicAdd(grad_rec + (size_t)s_id[stage][j] * GRAD_STRIDE + my_slot, v[0]);
             }
-            warp_transpose_reduce<NV>(v, lane);
-            if (my_slot >= 0) atomicAdd(grad_rec + (size_t)s_id[stage][j] * GRAD_STRIDE + my_slot, v[0]);
         }
+        if (more) stage_write((i + 1) & 1, have_next, rid, r0, r1, r2);
     }
-    cp_async_wait<0>();
 }
 
 int launch_blend_bwd(cudaStream_t s, int W, int H, int channels, const char* geom,

@@ -131,6 +131,37 @@ __device__ __forceinline__ void tile_pixel(uint32_t tid, uint32_t& lx, uint32_t&
     ly = ((warp >> 1) << 2) | (lane >> 3);
 }
 
+// Exact, conservative tile culling.  Can the Gaussian (mean m, conic (A, B, C), opacity op) reach
+// alpha >= 1/255 at ANY point of the pixel rectangle [x0,x1] x [y0,y1]?  alpha = op * exp(-q/2) with
+// q(d) = A dx^2 + 2 B dx dy + C dy^2 positive definite, so the question is whether
+// min_rect q <= 2 ln(255 op).  The minimiser over the rectangle is the centre when it lies inside,
+// otherwise it lies on an edge facing the centre (at most two), where q restricted to the edge is
+// a 1-D parabola whose clamped minimum is closed-form.  The reference has every pixel of the tile
+// evaluate and reject such Gaussians one by one (forward.cu:361-372); skipping them for the whole
+// tile cannot change any pixel.  A margin of 0.05 on the exponent covers the rounding of this
+// bound versus the per-pixel expression; NaNs compare false and keep the entry.
+__device__ __forceinline__ bool tile_may_contribute(float mx, float my, float A, float B, float C, float op,
+                                                    float x0, float y0, float x1, float y1) {
+    const float ex = fminf(fmaxf(mx, x0), x1), ey = fminf(fmaxf(my, y0), y1);
+    const float dxe = ex - mx, dye = ey - my;          // zero when the centre is inside in that dimension
+    float qmin = 0.f;
+    if (dxe != 0.f || dye != 0.f) {
+        qmin = 3.0e38f;
+        if (dxe != 0.f) {                               // facing vertical edge x = ex
+            const float ys = fminf(fmaxf(my - __fdividef(B * dxe, C), y0), y1);
+            const float dy = ys - my;
+            qmin = fminf(qmin, A * dxe * dxe + 2.f * B * dxe * dy + C * dy * dy);
+        }
+        if (dye != 0.f) {                               // facing horizontal edge y = ey
+            const float xs = fminf(fmaxf(mx - __fdividef(B * dye, A), x0), x1);
+            const float dx = xs - mx;
+            qmin = fminf(qmin, A * dx * dx + 2.f * B * dx * dye + C * dye * dye);
+        }
+    }
+    const float thr = -__logf(255.f * op);             // alpha >= 1/255  <=>  power >= thr
+    return !(-0.5f * qmin + 0.05f < thr);
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
