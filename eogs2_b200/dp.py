@@ -1,0 +1,136 @@
+"""Data parallelism over views for the rasterizer path.
+
+The reference trains on one GPU, one camera per optimiser step (train_pan.py:236-670,
+utils/general_utils.py:155 pins cuda:0) and has no communication code.  Views are independent
+units of work, so the path shards naturally: Gaussians are replicated, rank r rasterises the
+cameras r, r+k, r+2k, ... of the iteration's view batch (forward + backward), and there is ONE
+exchange step per iteration — an all-reduce (SUM) of a single flat fp32 bucket holding the
+gradients of the Adam parameter groups (xyz 3, f_dc 3, opacity 1, scaling 3, rotation 4 =
+14 floats per Gaussian, scene/gaussian_model.py:228-259) plus the camera-matrix gradients —
+before the replicated optimiser step.  One process per GPU (torchrun), `torch.distributed` with
+the NCCL backend over NVLink 5 / NVSwitch on a B200 box; the same code runs on `gloo` for the
+CPU tests.  A k-GPU step equals a 1-GPU step that accumulates the same k views (up to the
+all-reduce's summation order).
+
+Nothing here touches the kernels: `render_fn(params, camera) -> loss` is whatever the caller
+uses (the EOGS++ render() + losses, or bench.py's synthetic loss).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+PARAM_ORDER = ("xyz", "f_dc", "opacity", "scaling", "rotation")   # Adam groups, gaussian_model.py:228-259
+
+
+def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
+    """Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun); returns (rank, world, local_rank)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def shard_views(num_views: int, rank: int, world: int) -> List[int]:
+    """Round-robin ownership of the iteration's views: rank r takes r, r+world, ..."""
+    return list(range(rank, num_views, world))
+
+
+@dataclass
+class GradBucket:
+    """One flat fp32 buffer for every gradient that must be exchanged, laid out as
+    [xyz | f_dc | opacity | scaling | rotation | extras...]: a single collective per step."""
+    params: Dict[str, torch.Tensor]
+    extras: Dict[str, torch.Tensor] = field(default_factory=dict)   # e.g. per-camera viewmatrix params
+
+    def __post_init__(self):
+        self.names = [n for n in PARAM_ORDER if n in self.params] + \
+                     sorted(n for n in self.params if n not in PARAM_ORDER)
+        self.slices = {}
+        off = 0
+        for n in self.names:
+            k = self.params[n].numel()
+            self.slices[n] = (off, off + k)
+            off += k
+        for n in sorted(self.extras):
+            k = self.extras[n].numel()
+            self.slices["extra:" + n] = (off, off + k)
+            off += k
+        any_p = next(iter(self.params.values()))
+        self.flat = torch.zeros(off, dtype=torch.float32, device=any_p.device)
+
+    def pack(self) -> torch.Tensor:
+        for n in self.names:
+            a, b = self.slices[n]
+            g = self.params[n].grad
+            if g is None:
+                self.flat[a:b].zero_()
+            else:
+                self.flat[a:b].copy_(g.reshape(-1))
+        for n, t in self.extras.items():
+            a, b = self.slices["extra:" + n]
+            if t.grad is None:
+                self.flat[a:b].zero_()
+            else:
+                self.flat[a:b].copy_(t.grad.reshape(-1))
+        return self.flat
+
+    def all_reduce(self, average: bool = False) -> torch.Tensor:
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            if average:
+                self.flat.div_(dist.get_world_size())
+        return self.flat
+
+    def unpack(self) -> None:
+        for n in self.names:
+            a, b = self.slices[n]
+            p = self.params[n]
+            p.grad = self.flat[a:b].view_as(p).clone()
+        for n, t in self.extras.items():
+            a, b = self.slices["extra:" + n]
+            t.grad = self.flat[a:b].view_as(t).clone()
+
+
+def dp_backward(params: Dict[str, torch.Tensor], cameras: Sequence, render_fn: Callable,
+                rank: int, world: int, bucket: GradBucket | None = None, average: bool = False) -> float:
+    """One data-parallel gradient evaluation: this rank renders its share of `cameras` forward +
+    backward (gradients accumulate in .grad), then the bucket is all-reduced and written back so
+    that every rank holds the gradient of sum_views loss — what a single GPU would have after
+    accumulating all the views.  Returns this rank's summed loss."""
+    for p in params.values():
+        p.grad = None
+    if bucket is not None:
+        for t in bucket.extras.values():
+            t.grad = None
+    total = 0.0
+    for i in shard_views(len(cameras), rank, world):
+        loss = render_fn(params, cameras[i])
+        loss.backward()
+        total += float(loss.detach())
+    if bucket is None:
+        bucket = GradBucket(params)
+    bucket.pack()
+    bucket.all_reduce(average)
+    bucket.unpack()
+    return total
+
+
+def replicated_adam(params: Dict[str, torch.Tensor], lrs: Dict[str, float]) -> torch.optim.Optimizer:
+    """Adam with eps = 1e-15 and one group per parameter, as GaussianModel.training_setup
+    (scene/gaussian_model.py:228-262).  Every rank steps the same optimiser on the same reduced
+    gradients, so parameters stay bit-identical across ranks without a broadcast."""
+    groups = [{"params": [params[n]], "lr": lrs.get(n, 1e-3), "name": n} for n in params]
+    return torch.optim.Adam(groups, lr=0.0, eps=1e-15)
