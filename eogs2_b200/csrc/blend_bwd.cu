@@ -12,21 +12,20 @@
 //
 // Other differences from the reference kernel
 //   - the replay starts at the tile's max(n_contrib) instead of the end of the list, so list
-//     entries nobody blended are never fetched (the reference stages and skips them);
+//     entries nobody blended are never fetched (the reference stages and skips them); a warp
+//     additionally never sees entries beyond its own 32 pixels' max(n_contrib);
+//   - exact tile / warp-patch culling with per-warp entry lists and a register-prefetch pipeline
+//     with one barrier per batch, exactly as in the forward (blend_common.cuh);
 //   - the per-channel accum_rec / last_color recurrences (backward.cu:584-596) are collapsed
 //     into one scalar recurrence on the dot product with dL_dpixel (same linear map);
 //   - dL_dinvdepth per Gaussian is not accumulated: the reference computes it and drops it
-//     (backward.cu:305-307 commented out; it never reaches a returned gradient);
-//   - exact tile culling + warp-segment compaction at staging time and a register-prefetch
-//     pipeline with one barrier per batch, exactly as in blend_fwd.cu.
+//     (backward.cu:305-307 commented out; it never reaches a returned gradient).
 //
-// Bound: FP32 issue + shuffle + L2 reduction throughput.  Algorithmic HBM bytes: 52 B gathered +
-// <= 8 warps x 44 B reduced per instance, 4*(C+1) + 8 B per pixel in.
-#include "common.cuh"
+// Bound: FP32 issue + shuffle.  Algorithmic HBM bytes: 52 B gathered + <= 8 warps x 44 B reduced per
+// instance, 4*(C+1) + 8 B per pixel in.
+#include "blend_common.cuh"
 
 namespace eogs {
-
-constexpr int BWD_THREADS = TILE_PIXELS;
 
 // Transposing butterfly level: N live values -> ceil(N/2), partner = lane ^ (1 << BIT).
 template <int N, int BIT>
@@ -70,8 +69,14 @@ __device__ __forceinline__ void warp_transpose_reduce(float* v, uint32_t lane) {
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+__device__ __forceinline__ float fast_rcp(float x) {      // x in [0.01, 1]: no denormal handling needed
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int C>
-__global__ void __launch_bounds__(BWD_THREADS)
+__global__ void __launch_bounds__(BLEND_THREADS, 4)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ splat, const float* __restrict__ bg, int W, int H,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -79,12 +84,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  float* __restrict__ grad_rec)
 {
     constexpr int NV = 6 + C;   // mean2D.xy, conic.xyw, opacity, colours
-    constexpr int NWARPS = BWD_THREADS / 32;
-    __shared__ float4 s_rec[2][REC_F4][BWD_THREADS];
-    __shared__ uint32_t s_id[2][BWD_THREADS];
-    __shared__ uint16_t s_pos[2][BWD_THREADS];
-    __shared__ int s_cnt[2][NWARPS];
-    __shared__ int s_nmax;
+    __shared__ BlendStage s_stage[2];
+    __shared__ uint32_t s_id[2][BLEND_THREADS];
+    __shared__ int s_wmax[BLEND_WARPS];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint32_t lx, ly;
@@ -94,49 +96,41 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const size_t pix_id = (size_t)pix_y * W + pix_x;
     const float pixfx = (float)pix_x, pixfy = (float)pix_y;
     const float tx0 = (float)(blockIdx.x * TILE), ty0 = (float)(blockIdx.y * TILE);
-    const float tx1 = fminf(tx0 + (TILE - 1), (float)(W - 1)), ty1 = fminf(ty0 + (TILE - 1), (float)(H - 1));
+    const float img_x1 = (float)(W - 1), img_y1 = (float)(H - 1);
 
     const uint2 range = __ldg(ranges + blockIdx.y * gridDim.x + blockIdx.x);
     const uint32_t* list = point_list + range.x;
 
     const int last_contributor = inside ? (int)__ldg(n_contrib + pix_id) : 0;
-    if (tid == 0) s_nmax = 0;
-    __syncthreads();
     const int wmax = __reduce_max_sync(0xffffffffu, last_contributor);
-    if (lane == 0 && wmax > 0) atomicMax(&s_nmax, wmax);
+    if (lane == 0) s_wmax[warp] = wmax;
     __syncthreads();
-    const int nmax = s_nmax;            // entries [nmax, n) were blended by no pixel of this tile
+    int nmax = 0;                        // entries [nmax, n) were blended by no pixel of this tile
+#pragma unroll
+    for (int w = 0; w < BLEND_WARPS; w++) nmax = max(nmax, s_wmax[w]);
     if (nmax == 0) return;
-    const int rounds = (nmax + BWD_THREADS - 1) / BWD_THREADS;
+    const int rounds = (nmax + BLEND_THREADS - 1) / BLEND_THREADS;
 
     // Batch b, thread t holds list position nmax-1 - (b*256 + t): back to front.
-    auto list_pos = [&](int batch) { return nmax - 1 - (batch * BWD_THREADS + (int)tid); };
-    auto fetch = [&](uint32_t id, float4& r0, float4& r1, float4& r2) {
-        const float4* src = splat + (size_t)id * REC_F4;
-        r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2);
-    };
-    // cull + compact (same exact tile test as the forward, so the same entries survive)
-    auto stage_write = [&](int stage, bool have, uint32_t id, const float4& r0, const float4& r1, const float4& r2) {
-        const bool keep = have && tile_may_contribute(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tx0, ty0, tx1, ty1);
-        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            const uint32_t slot = warp * 32u + __popc(ballot & ((1u << lane) - 1u));
-            s_rec[stage][0][slot] = r0;
-            s_rec[stage][1][slot] = r1;
-            s_rec[stage][2][slot] = r2;
-            s_id[stage][slot] = id;
-            s_pos[stage][slot] = (uint16_t)tid;
-        }
-        if (lane == 0) s_cnt[stage][warp] = __popc(ballot);
+    auto list_pos = [&](int batch) { return nmax - 1 - (batch * BLEND_THREADS + (int)tid); };
+    // patches whose pixels all stopped before list position p never replay it
+    auto mask_for = [&](int p, const float4& r0, const float4& r1) {
+        uint32_t m = patch_mask(r0, r1, tx0, ty0, img_x1, img_y1);
+#pragma unroll
+        for (int w = 0; w < BLEND_WARPS; w++)
+            if (p >= s_wmax[w]) m &= ~(1u << w);
+        return m;
     };
 
     float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
     uint32_t rid = 0, id_next = 0;
     {   // prologue: batch 0 staged, ids of batch 1 in registers
-        const bool have = list_pos(0) >= 0;
-        if (have) { rid = __ldg(list + list_pos(0)); fetch(rid, r0, r1, r2); }
+        const int p = list_pos(0);
+        if (p >= 0) { rid = __ldg(list + p); fetch_record(splat, rid, r0, r1, r2); }
         if (list_pos(1) >= 0) id_next = __ldg(list + list_pos(1));
-        stage_write(0, have, rid, r0, r1, r2);
+        const uint32_t m = p >= 0 ? mask_for(p, r0, r1) : 0u;
+        if (m) s_id[0][tid] = rid;
+        stage_entry(s_stage[0], tid, m, r0, r1, r2);
     }
 
     const float T_final = inside ? __ldg(final_T + pix_id) : 0.f;
@@ -157,23 +151,24 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     for (int i = 0; i < rounds; i++) {
         __syncthreads();                 // stage i&1 complete; the other stage is free again
         const bool more = i + 1 < rounds;
-        const bool have_next = more && list_pos(i + 1) >= 0;
-        if (have_next) { rid = id_next; fetch(rid, r0, r1, r2); }  // in flight during the replay below
+        const int p_next = list_pos(i + 1);
+        const bool have_next = more && p_next >= 0;
+        if (have_next) { rid = id_next; fetch_record(splat, rid, r0, r1, r2); }   // in flight during the replay below
         if (list_pos(i + 2) >= 0) id_next = __ldg(list + list_pos(i + 2));
 
         const int stage = i & 1;
-        const int first = nmax - 1 - i * BWD_THREADS;              // list position of batch slot 0
-        for (int seg = 0; seg < NWARPS; seg++) {
-            const int cnt = s_cnt[stage][seg];
-            const int base = seg * 32;
-            for (int j = base; j < base + cnt; j++) {
+        const BlendStage& st = s_stage[stage];
+        const int first = nmax - 1 - i * BLEND_THREADS;            // list position of batch slot 0
+        for (int seg = 0; seg < BLEND_WARPS; seg++) {
+            const int cnt = st.cnt[warp][seg];
+            for (int j = 0; j < cnt; j++) {
+                const uint32_t e = st.list[warp][seg][j];
                 // Entry at list position p is blended by this pixel iff p < n_contrib (backward.cu:556-558).
-                const bool active = (first - (int)s_pos[stage][j]) < last_contributor;
-                const float4 ra = s_rec[stage][0][j];
-                const float4 rb = s_rec[stage][1][j];
-                const float dx = __fsub_rn(ra.x, pixfx), dy = __fsub_rn(ra.y, pixfy);
-                const float quad = __fmaf_rn(dx, __fmul_rn(ra.z, dx), __fmul_rn(__fmul_rn(rb.x, dy), dy));
-                const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx), dy));
+                const bool active = (first - (int)e) < last_contributor;
+                const float4 ra = st.rec[0][e];
+                const float4 rb = st.rec[1][e];
+                float dx, dy;
+                const float power = pair_power(ra, rb, pixfx, pixfy, dx, dy);
                 const float G = expf(power);
                 const float alpha = fminf(0.99f, __fmul_rn(rb.y, G));
                 const bool valid = active && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
@@ -183,9 +178,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #pragma unroll
                 for (int k = 0; k < NV; k++) v[k] = 0.f;
                 if (valid) {
-                    const float4 rc = s_rec[stage][2][j];
+                    const float4 rc = st.rec[2][e];
                     const float col[5] = {rb.z, rb.w, rc.x, rc.y, rc.z};
-                    const float inv_1ma = __fdividef(1.f, 1.f - alpha);
+                    const float inv_1ma = fast_rcp(1.f - alpha);
                     T *= inv_1ma;
                     const float w = alpha * T;
                     float cg = rc.w * g_inv;
@@ -212,10 +207,14 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     v[5] = G * dL_dalpha;
                 }
                 warp_transpose_reduce<NV>(v, lane);
-                if (my_slot >= 0) atomicAdd(grad_rec + (size_t)s_id[stage][j] * GRAD_STRIDE + my_slot, v[0]);
+                if (my_slot >= 0) atomicAdd(grad_rec + (size_t)s_id[stage][e] * GRAD_STRIDE + my_slot, v[0]);
             }
         }
-        if (more) stage_write((i + 1) & 1, have_next, rid, r0, r1, r2);
+        if (more) {
+            const uint32_t m = have_next ? mask_for(p_next, r0, r1) : 0u;
+            if (m) s_id[(i + 1) & 1][tid] = rid;
+            stage_entry(s_stage[(i + 1) & 1], tid, m, r0, r1, r2);
+        }
     }
 }
 
@@ -226,7 +225,7 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, int channels, const char* geo
 {
     const dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
     auto run = [&](auto kernel) {
-        kernel<<<grid, BWD_THREADS, 0, s>>>(
+        kernel<<<grid, BLEND_THREADS, 0, s>>>(
             reinterpret_cast<const uint2*>(image + IL.ranges), point_list,
             reinterpret_cast<const float4*>(geom + GL.splat), bg, W, H,
             reinterpret_cast<const float*>(image + IL.final_T),

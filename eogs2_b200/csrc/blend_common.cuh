@@ -1,0 +1,119 @@
+// Staging machinery shared by the forward and backward blend kernels.
+//
+// A 256-thread CTA owns a 16x16 tile; warp w owns the 8x4 pixel patch
+//     x in [tile_x + 8*(w&1), +7],  y in [tile_y + 4*(w>>1), +3]          (tile_pixel, common.cuh)
+// Per batch of 256 list entries, thread t fetches entry t's packed record and decides, once, which
+// of the 8 warp patches the Gaussian can reach with alpha >= 1/255 (tile_may_contribute on the tile,
+// then on each patch): an 8-bit mask.  The record is stored at slot t of the batch's shared-memory
+// stage and t is appended — in list order — to the private entry list of every warp whose bit is set
+// (warp ballots; per-(consumer warp, staging warp) segments so no cross-warp prefix sum and no extra
+// barrier is needed).  The consumer warps then iterate only over entries that can touch their own
+// 32 pixels.  The reference evaluates every entry of the tile list in every one of the 256 threads
+// (forward.cu:356-372, backward.cu:551-577).  Culling is exact and conservative: it only removes
+// (pixel, Gaussian) pairs that the per-pixel test would reject, so images, n_contrib and gradients
+// are unchanged; the tile lists themselves stay the reference's.
+#pragma once
+#include "common.cuh"
+
+namespace eogs {
+
+constexpr int BLEND_THREADS = TILE_PIXELS;          // 256
+constexpr int BLEND_WARPS = BLEND_THREADS / 32;     // 8
+constexpr int PATCH_W = 8, PATCH_H = 4;
+
+struct BlendStage {
+    float4 rec[REC_F4][BLEND_THREADS];                       // packed records, slot = position in batch
+    uint8_t list[BLEND_WARPS][BLEND_WARPS][32];              // [consumer warp][staging warp][rank] -> slot
+    uint8_t cnt[BLEND_WARPS][BLEND_WARPS];                   // [consumer warp][staging warp]
+};
+
+// 8-bit mask of the warp patches this Gaussian may contribute to (bit w = patch of warp w).
+//
+// alpha >= 1/255 somewhere in a patch  <=>  the ellipse E = { p : q(p - m) <= qmax },
+// qmax = 2 ln(255 op), meets the patch rectangle.  E is cut by horizontal lines at the patch-row
+// boundaries: on a line at offset dy from the centre, E spans x in [c - h, c + h] with
+// c = mx - (B/A) dy and h = sqrt(A qmax - det dy^2) / A.  Over a band between two lines the
+// right edge c + h is concave in dy, so its maximum is the bounding-box extreme mx + hx when the
+// extreme's dy = -(B/C) hx lies inside the band and otherwise sits on one of the two lines;
+// same for the left edge.  One sqrt per line (5 lines for 4 bands, bands widened by half a pixel
+// so neighbours share a line) gives all 8 answers exactly, for ~1/3 of the cost of eight independent
+// rectangle tests.  Margin 0.1 on q (0.05 on the exponent) covers rounding and the approximate
+// sqrt / divide; NaNs compare false and keep the entry.
+__device__ __forceinline__ uint32_t patch_mask(const float4& r0, const float4& r1, float tx0, float ty0,
+                                               float img_x1, float img_y1) {
+    constexpr int ROWS = TILE / PATCH_H, COLS = TILE / PATCH_W;
+    const float mx = r0.x, my = r0.y, A = r0.z, B = r0.w, C = r1.x, op = r1.y;
+    const float qmax = 2.f * __logf(255.f * op) + 0.1f;
+    if (qmax <= 0.f) return 0u;
+    const float det = A * C - B * B;
+    const float inv_det = __fdividef(1.f, det), invA = __fdividef(1.f, A);
+    const float hx = __fsqrt_rn(qmax * C * inv_det), hy = __fsqrt_rn(qmax * A * inv_det);
+    // whole-tile reject (also the common case): bounding box of E vs the tile
+    if (mx + hx < tx0 || mx - hx > tx0 + (TILE - 1) || my + hy < ty0 || my - hy > ty0 + (TILE - 1)) return 0u;
+    const float slope = -B * invA;
+    const float dy_right = __fdividef(-B * hx, C), dy_left = -dy_right;
+    const float Aq = A * qmax;
+
+    float dyl[ROWS + 1], xr[ROWS + 1], xl[ROWS + 1];
+#pragma unroll
+    for (int k = 0; k <= ROWS; k++) {
+        dyl[k] = (ty0 + (float)(PATCH_H * k) - 0.5f) - my;
+        const float dyc = fminf(fmaxf(dyl[k], -hy), hy);
+        const float h = __fsqrt_rn(fmaxf(0.f, Aq - det * dyc * dyc)) * invA;
+        const float c = mx + slope * dyc;
+        xr[k] = c + h;
+        xl[k] = c - h;
+    }
+    uint32_t m = 0u;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        if (dyl[r + 1] < -hy || dyl[r] > hy) continue;                      // band misses E in y
+        if (ty0 + (float)(PATCH_H * r) > img_y1) continue;                  // band below the image
+        const float right = (dy_right > dyl[r] && dy_right < dyl[r + 1]) ? mx + hx : fmaxf(xr[r], xr[r + 1]);
+        const float left = (dy_left > dyl[r] && dy_left < dyl[r + 1]) ? mx - hx : fminf(xl[r], xl[r + 1]);
+#pragma unroll
+        for (int c = 0; c < COLS; c++) {
+            const float px0 = tx0 + (float)(PATCH_W * c);
+            if (px0 > img_x1) continue;
+            if (!(right < px0 - 0.01f || left > px0 + (PATCH_W - 1) + 0.01f)) m |= 1u << (r * COLS + c);
+        }
+    }
+    return m;
+}
+
+// Warp-collective: store this thread's record at slot tid and append tid to the consumer lists.
+__device__ __forceinline__ void stage_entry(BlendStage& st, uint32_t tid, uint32_t mask,
+                                            const float4& r0, const float4& r1, const float4& r2) {
+    const uint32_t lane = tid & 31u, swarp = tid >> 5;
+    if (mask) {
+        st.rec[0][tid] = r0;
+        st.rec[1][tid] = r1;
+        st.rec[2][tid] = r2;
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int w = 0; w < BLEND_WARPS; w++) {
+        const bool mine = (mask >> w) & 1u;
+        const uint32_t ballot = __ballot_sync(0xffffffffu, mine);
+        if (mine) st.list[w][swarp][__popc(ballot & lt)] = (uint8_t)tid;
+        if (lane == (uint32_t)w) st.cnt[w][swarp] = (uint8_t)__popc(ballot);
+    }
+}
+
+__device__ __forceinline__ void fetch_record(const float4* __restrict__ splat, uint32_t id,
+                                             float4& r0, float4& r1, float4& r2) {
+    const float4* src = splat + (size_t)id * REC_F4;
+    r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2);
+}
+
+// The reference's per-pair exponent, in the op order of its sm_100a SASS (forward.cu:361-365):
+// power = -0.5f * (con.x*dx*dx + con.z*dy*dy) - con.y*dx*dy
+__device__ __forceinline__ float pair_power(const float4& ra, const float4& rb, float pixfx, float pixfy,
+                                            float& dx, float& dy) {
+    dx = __fsub_rn(ra.x, pixfx);
+    dy = __fsub_rn(ra.y, pixfy);
+    const float quad = __fmaf_rn(dx, __fmul_rn(ra.z, dx), __fmul_rn(__fmul_rn(rb.x, dy), dy));
+    return __fmaf_rn(quad, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx), dy));
+}
+
+}  // namespace eogs
