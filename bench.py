@@ -274,6 +274,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the e2e leg (the line then carries e2e=null)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_env()
@@ -391,7 +392,9 @@ def main():
 
     # e2e through the public API with host inputs
     e2e_step, h2d, d2h = ours_e2e_factory(wl, dev)
-    e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, world)
+    e2e_ms = None
+    if not args.no_e2e:
+        e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, world)
 
     value = world * args.steps / (total_ms / 1e3)
     # roofline of the dominant kernel: blend backward.  Algorithmic bytes per launch:
@@ -401,7 +404,7 @@ def main():
     bwd_ms = stage_ms[STAGES.index("blend_bwd")]
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
     line = dict(base, value=value, ms_per_step=total_ms / args.steps, clocks=clocks,
-                e2e={"value": world * args.steps / (e2e_ms / 1e3), "unit": "renders/s",
+                e2e=None if e2e_ms is None else {"value": world * args.steps / (e2e_ms / 1e3), "unit": "renders/s",
                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 gpu_launches=7 * args.steps,
                 roofline={"kernel": "blend_bwd_kernel<5>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
