@@ -134,3 +134,55 @@ def replicated_adam(params: Dict[str, torch.Tensor], lrs: Dict[str, float]) -> t
     gradients, so parameters stay bit-identical across ranks without a broadcast."""
     groups = [{"params": [params[n]], "lr": lrs.get(n, 1e-3), "name": n} for n in params]
     return torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+
+
+class HostInputPipeline:
+    """Double-buffered host -> device staging of a step's input tensors.
+
+    `submit(host_tensors)` enqueues the copies of the NEXT step's pinned host tensors on a side
+    stream into one of two preallocated device slots; `get()` makes the current stream wait for
+    them and returns the device tensors.  Calling `get()` then `submit()` at the top of every step
+    overlaps the PCIe transfer of step s+1 with the kernels of step s.  Plain torch plumbing
+    (streams + events): it knows nothing about the rasterizer and works for any dict of tensors.
+
+    A slot is overwritten two submits later; the copy first waits (on the device) for everything
+    the consumer stream had enqueued when the following `get()` was called, so the usual
+    "use the tensors within the step" pattern is race-free.
+    """
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device)
+        self.slots: List[Dict[str, torch.Tensor] | None] = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [None, None]             # event on the consumer stream after which the slot may be rewritten
+        self.next_slot = 0
+        self.pending: List[int] = []
+
+    def submit(self, host_tensors: Dict[str, torch.Tensor]) -> None:
+        s = self.next_slot
+        self.next_slot ^= 1
+        if self.slots[s] is None or any(self.slots[s][k].shape != v.shape or self.slots[s][k].dtype != v.dtype
+                                        for k, v in host_tensors.items()):
+            with torch.cuda.device(self.device):
+                self.slots[s] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                                 for k, v in host_tensors.items()}
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[s] is not None:
+                self.copy_stream.wait_event(self.free[s])
+            for k, v in host_tensors.items():
+                self.slots[s][k].copy_(v, non_blocking=True)
+            self.ready[s].record(self.copy_stream)
+        self.pending.append(s)
+
+    def get(self) -> Dict[str, torch.Tensor]:
+        if not self.pending:
+            raise RuntimeError("HostInputPipeline.get() without a pending submit()")
+        s = self.pending.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(self.ready[s])
+        # the OTHER slot's previous consumer work is already enqueued on `cur`: mark it reusable
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.free[s ^ 1] = ev
+        return self.slots[s]

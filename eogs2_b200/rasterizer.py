@@ -60,8 +60,8 @@ class ForwardState:
     point_list: Optional[torch.Tensor]
     image: Optional[torch.Tensor]
     radii: torch.Tensor
-    color: torch.Tensor
-    invdepth: torch.Tensor
+    color: Optional[torch.Tensor]
+    invdepth: Optional[torch.Tensor]
 
 
 _pinned_info: dict = {}
@@ -293,9 +293,16 @@ class _RasterizeGaussians(torch.autograd.Function):
             cov3Ds_precomp, viewmat, rs.image_height, rs.image_width, rs.antialiasing, rs.debug)
         ctx.raster_settings = rs
         ctx.num_rendered = state.num_rendered
-        ctx.state = state
+        # Keep only what the backward reads.  The output images must NOT be reachable from ctx:
+        # color.grad_fn is this node, so ctx -> state -> color would be a reference cycle that only
+        # Python's cyclic GC frees, and every step would then cudaMalloc fresh buffers.
+        ctx.state = ForwardState(state.P, state.W, state.H, state.channels, state.num_rendered,
+                                 state.geom, state.point_list, state.image, state.radii, None, None)
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, opacities)
         ctx.mark_non_differentiable(state.radii)
+        # An unused output (EOGS never reads invdepths) then arrives as None in backward instead of a
+        # materialised zero image (rasterize_points.cu:177-183 always gets one); same gradients.
+        ctx.set_materialize_grads(False)
         return state.color, state.radii, state.invdepth
 
     @staticmethod
@@ -303,6 +310,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         colors_precomp, means3D, scales, rotations, cov3Ds_precomp, opacities = ctx.saved_tensors
         state = ctx.state
+        if grad_out_color is None:
+            grad_out_color = torch.zeros((state.channels, state.H, state.W), dtype=torch.float32,
+                                         device=means3D.device)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp,
          grad_scales, grad_rotations, cam_sums) = rasterize_backward_raw(
             state, rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier,
