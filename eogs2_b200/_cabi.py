@@ -42,6 +42,25 @@ SIGNATURES = {
         c_ptr, c_ptr, c_ptr, c_ptr, c_f32p, c_f32p,                # radii, geom, point_list, image, dL_dpix, dL_dinvdepth
         c_f32p,                                                    # grad_scratch
         c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "eogs_image_bytes_band": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "eogs_forward_geometry_band": (C.c_int, [
+        c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,   # stream, P, W, H, channels, row_begin, row_end
+        c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
+        c_f32p, C.c_float, C.c_int,
+        c_ptr, c_ptr, c_ptr, c_ptr]),
+    "eogs_forward_render_band": (C.c_int, [
+        c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+        c_ptr, c_ptr, c_ptr, c_ptr, c_f32p, c_f32p, c_f32p]),
+    "eogs_backward_band": (C.c_int, [
+        c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+        c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,
+        c_f32p, c_f32p, C.c_float, C.c_int, c_f32p,
+        c_ptr, c_ptr, c_ptr, c_ptr, c_f32p, c_f32p,
+        c_f32p,
+        c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "eogs_export_state_band": (C.c_int, [
+        c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, c_ptr, c_ptr, c_ptr,
+        c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "eogs_mark_visible": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_f32p, c_ptr]),
     "eogs_profile_enable": (C.c_int, [C.c_int]),
     "eogs_profile_read": (C.c_int, [c_ptr, C.c_int]),
@@ -50,7 +69,7 @@ SIGNATURES = {
         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 

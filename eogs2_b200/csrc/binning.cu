@@ -40,10 +40,21 @@ GeomLayout geom_layout(int P) {
     return L;
 }
 
-ImageLayout image_layout(int W, int H) {
+Band full_band(int H) { return Band{0, (H + TILE - 1) / TILE}; }
+
+int check_band(int H, Band band) {
+    const int grid_y = (H + TILE - 1) / TILE;
+    if (band.row_begin < 0 || band.row_end > grid_y || band.row_begin >= band.row_end) {
+        set_error("bad band: tile rows [%d, %d) of %d", band.row_begin, band.row_end, grid_y);
+        return -1;
+    }
+    return 0;
+}
+
+ImageLayout image_layout(int W, int H, Band band) {
     ImageLayout L;
-    const size_t n = (size_t)W * (size_t)H;
-    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * (size_t)((H + TILE - 1) / TILE);
+    const size_t n = (size_t)W * (size_t)band.height(H);
+    const size_t tiles = (size_t)((W + TILE - 1) / TILE) * (size_t)band.rows();
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     L.final_T = take(n * 4);
@@ -125,7 +136,7 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
 constexpr int EMIT_THREADS = 256;
 
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_instances_kernel(int P, int grid_x, const uint32_t* __restrict__ order,
+emit_instances_kernel(int P, int grid_x, uint32_t band_y0, const uint32_t* __restrict__ order,
                       const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect,
                       uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ ids)
 {
@@ -164,7 +175,7 @@ emit_instances_kernel(int P, int grid_x, const uint32_t* __restrict__ order,
         const uint32_t x0 = r.x & 0xFFFFu, y0 = r.x >> 16, x1 = r.y & 0xFFFFu;
         const uint32_t w = x1 - x0;
         const uint32_t ry = local / w, rx = local - ry * w;   // row-major over (y, x), rasterizer_impl.cu:96-99
-        tile_keys[block_start + t] = (y0 + ry) * (uint32_t)grid_x + (x0 + rx);
+        tile_keys[block_start + t] = (y0 - band_y0 + ry) * (uint32_t)grid_x + (x0 + rx);   // band-relative tile id
         ids[block_start + t] = s_id[lo];
     }
 }
@@ -196,12 +207,12 @@ static uint32_t higher_msb(uint32_t n) {
     return msb;
 }
 
-int launch_binning(cudaStream_t s, int P, int W, int H, uint32_t I, const char* geom,
+int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, const char* geom,
                    const GeomLayout& GL, uint32_t* point_list, char* binning,
                    const BinningLayout& BL, char* image, const ImageLayout& IL)
 {
-    const int grid_x = (W + TILE - 1) / TILE, grid_y = (H + TILE - 1) / TILE;
-    const uint32_t tiles = (uint32_t)grid_x * (uint32_t)grid_y;
+    const int grid_x = (W + TILE - 1) / TILE;
+    const uint32_t tiles = (uint32_t)grid_x * (uint32_t)band.rows();
     uint2* ranges = reinterpret_cast<uint2*>(image + IL.ranges);
     EOGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
     if (I == 0) return 0;
@@ -211,7 +222,7 @@ int launch_binning(cudaStream_t s, int P, int W, int H, uint32_t I, const char* 
     uint32_t* val_in = reinterpret_cast<uint32_t*>(binning + BL.val_in);
 
     emit_instances_kernel<<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(
-        P, grid_x, reinterpret_cast<const uint32_t*>(geom + GL.order),
+        P, grid_x, (uint32_t)band.row_begin, reinterpret_cast<const uint32_t*>(geom + GL.order),
         reinterpret_cast<const uint32_t*>(geom + GL.offsets),
         reinterpret_cast<const uint2*>(geom + GL.rect), key_in, val_in);
     EOGS_LAUNCH_CHECK("emit_instances_kernel");

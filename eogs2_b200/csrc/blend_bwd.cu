@@ -53,7 +53,7 @@ template <int C>
 __global__ void __launch_bounds__(BWD_THREADS, 4)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ splat, const float* __restrict__ bg, int W, int H,
-                 int tiles_x, int tiles_y,
+                 int tiles_x, int tiles_y, int band_row0, int band_h,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, const float* __restrict__ dL_dinvdepth,
                  float* __restrict__ grad_rec)
@@ -63,13 +63,15 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     __shared__ BwdWarpSmem s_warp[BWD_WARPS];
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int tile_x = (int)blockIdx.x * 2 + (int)(warp & 1u), tile_y = (int)blockIdx.y * 2 + (int)(warp >> 1);
-    if (tile_x >= tiles_x || tile_y >= tiles_y) return;          // whole warp leaves; no block barriers below
+    // tiles_y = tile rows of the band; brow = row inside the band, tile_y = row in the image
+    const int tile_x = (int)blockIdx.x * 2 + (int)(warp & 1u), brow = (int)blockIdx.y * 2 + (int)(warp >> 1);
+    if (tile_x >= tiles_x || brow >= tiles_y) return;            // whole warp leaves; no block barriers below
+    const int tile_y = brow + band_row0;
     BwdWarpSmem& sm = s_warp[warp];
 
     const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);
     const float img_x1 = (float)(W - 1), img_y1 = (float)(H - 1);
-    const uint2 range = __ldg(ranges + (size_t)tile_y * tiles_x + tile_x);
+    const uint2 range = __ldg(ranges + (size_t)brow * tiles_x + tile_x);
     const uint32_t* list = point_list + range.x;
 
     // ---- per-pixel state: pixel (patch p, lane) = (tile_x*16 + 8*(p&1) + (lane&7), tile_y*16 + 4*(p>>1) + (lane>>3))
@@ -90,7 +92,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         const int px = tile_x * TILE + PATCH_W * (p & 1) + (int)(lane & 7u);
         const int py = tile_y * TILE + PATCH_H * (p >> 1) + (int)(lane >> 3);
         const bool inside = px < W && py < H;
-        const size_t pix_id = (size_t)py * W + px;
+        const size_t pix_id = (size_t)(py - band_row0 * TILE) * W + px;     // band-compact buffers
         ncon[p] = inside ? (int)__ldg(n_contrib + pix_id) : 0;
         const float Tf = inside ? __ldg(final_T + pix_id) : 0.f;
         T[p] = Tf;
@@ -99,7 +101,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         float bg_dot_g = 0.f;
 #pragma unroll
         for (int ch = 0; ch < C; ch++) {
-            g[ch] = inside ? __ldg(dL_dpix + (size_t)ch * H * W + pix_id) : 0.f;
+            g[ch] = inside ? __ldg(dL_dpix + (size_t)ch * band_h * W + pix_id) : 0.f;
             bg_dot_g = fmaf(bgv[ch], g[ch], bg_dot_g);
         }
         const float g_inv = (inside && dL_dinvdepth) ? __ldg(dL_dinvdepth + pix_id) : 0.f;
@@ -230,18 +232,18 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     }
 }
 
-int launch_blend_bwd(cudaStream_t s, int W, int H, int channels, const char* geom,
+int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
                      const GeomLayout& GL, const uint32_t* point_list, const char* image,
                      const ImageLayout& IL, const float* bg, const float* dL_dpix,
                      const float* dL_dinvdepth, float* grad_rec)
 {
-    const int tiles_x = (W + TILE - 1) / TILE, tiles_y = (H + TILE - 1) / TILE;
+    const int tiles_x = (W + TILE - 1) / TILE, tiles_y = band.rows();
     const dim3 grid((tiles_x + 1) / 2, (tiles_y + 1) / 2, 1);
     auto run = [&](auto kernel) {
         kernel<<<grid, BWD_THREADS, 0, s>>>(
             reinterpret_cast<const uint2*>(image + IL.ranges), point_list,
             reinterpret_cast<const float4*>(geom + GL.splat), bg, W, H, tiles_x, tiles_y,
-            reinterpret_cast<const float*>(image + IL.final_T),
+            band.row_begin, band.height(H), reinterpret_cast<const float*>(image + IL.final_T),
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), dL_dpix, dL_dinvdepth, grad_rec);
     };
     if (channels == 5) run(blend_bwd_kernel<5>);

@@ -74,14 +74,14 @@ __global__ void export_geom_kernel(int P, const float4* __restrict__ splat, cons
     if (tiles_touched) tiles_touched[i] = tiles[i];
 }
 
-__global__ void export_keys_kernel(uint32_t num_tiles, const uint2* __restrict__ ranges,
+__global__ void export_keys_kernel(uint32_t num_tiles, uint32_t tile_base, const uint2* __restrict__ ranges,
                                    const uint32_t* __restrict__ point_list,
                                    const float* __restrict__ depth, uint64_t* keys) {
     const uint32_t tile = blockIdx.x;
     if (tile >= num_tiles) return;
     const uint2 r = ranges[tile];
     for (uint32_t j = r.x + threadIdx.x; j < r.y; j += blockDim.x)
-        keys[j] = ((uint64_t)tile << 32) | (uint64_t)__float_as_uint(depth[point_list[j]]);
+        keys[j] = ((uint64_t)(tile + tile_base) << 32) | (uint64_t)__float_as_uint(depth[point_list[j]]);
 }
 
 static int check_common(int P, int W, int H, int channels) {
@@ -121,10 +121,16 @@ EOGS_API int eogs_profile_read(float* ms, int n) {
 }
 
 EOGS_API size_t eogs_geom_bytes(int P) { return geom_layout(P).total; }
-EOGS_API size_t eogs_image_bytes(int W, int H) { return image_layout(W, H).total; }
+EOGS_API size_t eogs_image_bytes(int W, int H) { return image_layout(W, H, full_band(H)).total; }
+EOGS_API size_t eogs_image_bytes_band(int W, int H, int row_begin, int row_end) {
+    const Band b{row_begin, row_end};
+    if (W <= 0 || H <= 0 || check_band(H, b)) return 0;
+    return image_layout(W, H, b).total;
+}
 EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t I) { return binning_layout(W, H, I).total; }
 
-EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, int channels,
+EOGS_API int eogs_forward_geometry_band(eogs_stream_t stream, int P, int W, int H, int channels,
+                          int row_begin, int row_end,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities, const float* colors,
                           const float* viewmatrix, float scale_modifier, int antialiasing,
@@ -132,6 +138,8 @@ EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, in
                           eogs_forward_info* info_host)
 {
     if (int rc = check_common(P, W, H, channels)) return rc;
+    const Band band{row_begin, row_end};
+    if (int rc = check_band(H, band)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (!colors) { set_error("For non-RGB, provide precomputed Gaussian colors!"); return -4; }   // rasterizer_impl.cu:244-247
     if (!cov3D_precomp && (!scales || !rotations)) { set_error("need scales+rotations or cov3D_precomp"); return -4; }
@@ -141,7 +149,7 @@ EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, in
     if (P > 0) {
         const GeomLayout L = geom_layout(P);
         char* g = static_cast<char*>(geom);
-        if (int rc = launch_preprocess_fwd(s, P, W, H, channels, means3D, scales, rotations, cov3D_precomp,
+        if (int rc = launch_preprocess_fwd(s, P, W, H, band, channels, means3D, scales, rotations, cov3D_precomp,
                                            opacities, colors, viewmatrix, scale_modifier, antialiasing != 0,
                                            radii, g, L, info_dev)) return rc;
         prof_mark(s, ST_PREPROCESS);
@@ -152,24 +160,50 @@ EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, in
     return 0;
 }
 
+EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, int channels,
+                          const float* means3D, const float* scales, const float* rotations,
+                          const float* cov3D_precomp, const float* opacities, const float* colors,
+                          const float* viewmatrix, float scale_modifier, int antialiasing,
+                          int32_t* radii, void* geom, eogs_forward_info* info_dev,
+                          eogs_forward_info* info_host)
+{
+    if (int rc = check_common(P, W, H, channels)) return rc;
+    return eogs_forward_geometry_band(stream, P, W, H, channels, 0, (H + TILE - 1) / TILE, means3D, scales, rotations,
+                                      cov3D_precomp, opacities, colors, viewmatrix, scale_modifier, antialiasing,
+                                      radii, geom, info_dev, info_host);
+}
+
+EOGS_API int eogs_forward_render_band(eogs_stream_t stream, int P, int W, int H, int channels,
+                        int row_begin, int row_end,
+                        uint32_t num_instances, const void* geom, uint32_t* point_list,
+                        void* binning, void* image, const float* bg,
+                        float* out_color, float* out_invdepth)
+{
+    if (int rc = check_common(P, W, H, channels)) return rc;
+    const Band band{row_begin, row_end};
+    if (int rc = check_band(H, band)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!geom || !image || !bg || !out_color) { set_error("null argument"); return -4; }
+    if (num_instances > 0 && (!point_list || !binning)) { set_error("null binning buffers"); return -4; }
+    const GeomLayout GL = geom_layout(P);
+    const ImageLayout IL = image_layout(W, H, band);
+    const BinningLayout BL = binning_layout(W, H, num_instances);
+    if (int rc = launch_binning(s, P, W, H, band, num_instances, static_cast<const char*>(geom), GL, point_list,
+                                static_cast<char*>(binning), BL, static_cast<char*>(image), IL)) return rc;
+    if (int rc = launch_blend_fwd(s, W, H, band, channels, static_cast<const char*>(geom), GL, point_list,
+                                  static_cast<char*>(image), IL, bg, out_color, out_invdepth)) return rc;
+    prof_mark(s, ST_BLEND_FWD);
+    return 0;
+}
+
 EOGS_API int eogs_forward_render(eogs_stream_t stream, int P, int W, int H, int channels,
                         uint32_t num_instances, const void* geom, uint32_t* point_list,
                         void* binning, void* image, const float* bg,
                         float* out_color, float* out_invdepth)
 {
     if (int rc = check_common(P, W, H, channels)) return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (!geom || !image || !bg || !out_color) { set_error("null argument"); return -4; }
-    if (num_instances > 0 && (!point_list || !binning)) { set_error("null binning buffers"); return -4; }
-    const GeomLayout GL = geom_layout(P);
-    const ImageLayout IL = image_layout(W, H);
-    const BinningLayout BL = binning_layout(W, H, num_instances);
-    if (int rc = launch_binning(s, P, W, H, num_instances, static_cast<const char*>(geom), GL, point_list,
-                                static_cast<char*>(binning), BL, static_cast<char*>(image), IL)) return rc;
-    if (int rc = launch_blend_fwd(s, W, H, channels, static_cast<const char*>(geom), GL, point_list,
-                                  static_cast<char*>(image), IL, bg, out_color, out_invdepth)) return rc;
-    prof_mark(s, ST_BLEND_FWD);
-    return 0;
+    return eogs_forward_render_band(stream, P, W, H, channels, 0, (H + TILE - 1) / TILE, num_instances, geom,
+                                    point_list, binning, image, bg, out_color, out_invdepth);
 }
 
 EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, int channels,
@@ -211,8 +245,8 @@ EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, i
                                binning, *image, bg, out_color, out_invdepth);
 }
 
-EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channels,
-                  uint32_t num_instances,
+EOGS_API int eogs_backward_band(eogs_stream_t stream, int P, int W, int H, int channels,
+                  int row_begin, int row_end, uint32_t num_instances,
                   const float* means3D, const float* scales, const float* rotations,
                   const float* cov3D_precomp, const float* opacities, const float* colors,
                   const float* viewmatrix, const float* projmatrix,
@@ -226,6 +260,8 @@ EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channe
 {
     (void)colors;
     if (int rc = check_common(P, W, H, channels)) return rc;
+    const Band band{row_begin, row_end};
+    if (int rc = check_band(H, band)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (!cam_sums) { set_error("null argument"); return -4; }
     if (P == 0) { EOGS_CUDA(cudaMemsetAsync(cam_sums, 0, 16 * sizeof(float), s)); return 0; }
@@ -235,12 +271,12 @@ EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channe
     }
     if (!cov3D_precomp && (!scales || !rotations)) { set_error("need scales+rotations or cov3D_precomp"); return -4; }
     const GeomLayout GL = geom_layout(P);
-    const ImageLayout IL = image_layout(W, H);
+    const ImageLayout IL = image_layout(W, H, band);
     EOGS_CUDA(cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s));
     prof_mark(s, ST_BWD_ZERO);
     if (num_instances > 0) {
         if (!point_list) { set_error("null point_list"); return -4; }
-        if (int rc = launch_blend_bwd(s, W, H, channels, static_cast<const char*>(geom), GL, point_list,
+        if (int rc = launch_blend_bwd(s, W, H, band, channels, static_cast<const char*>(geom), GL, point_list,
                                       static_cast<const char*>(image), IL, bg, dL_dpix, dL_dinvdepth,
                                       grad_scratch)) return rc;
     }
@@ -251,6 +287,27 @@ EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channe
                                  dL_drotations, cam_sums);
     prof_mark(s, ST_PREPROCESS_BWD);
     return rc_pre;
+}
+
+EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channels,
+                  uint32_t num_instances,
+                  const float* means3D, const float* scales, const float* rotations,
+                  const float* cov3D_precomp, const float* opacities, const float* colors,
+                  const float* viewmatrix, const float* projmatrix,
+                  float scale_modifier, int antialiasing, const float* bg,
+                  const int32_t* radii, const void* geom, const uint32_t* point_list,
+                  const void* image, const float* dL_dpix, const float* dL_dinvdepth,
+                  float* grad_scratch,
+                  float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                  float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                  float* dL_drotations, float* cam_sums)
+{
+    if (int rc = check_common(P, W, H, channels)) return rc;
+    return eogs_backward_band(stream, P, W, H, channels, 0, (H + TILE - 1) / TILE, num_instances, means3D, scales,
+                              rotations, cov3D_precomp, opacities, colors, viewmatrix, projmatrix, scale_modifier,
+                              antialiasing, bg, radii, geom, point_list, image, dL_dpix, dL_dinvdepth, grad_scratch,
+                              dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales,
+                              dL_drotations, cam_sums);
 }
 
 EOGS_API int eogs_mark_visible(eogs_stream_t stream, int P, const float* means3D,
@@ -265,18 +322,23 @@ EOGS_API int eogs_mark_visible(eogs_stream_t stream, int P, const float* means3D
     return 0;
 }
 
-EOGS_API int eogs_export_state(eogs_stream_t stream, int P, int W, int H, uint32_t num_instances,
-                      const void* geom, const uint32_t* point_list, const void* image,
+EOGS_API int eogs_export_state_band(eogs_stream_t stream, int P, int W, int H, int row_begin, int row_end,
+                      uint32_t num_instances, const void* geom, const uint32_t* point_list, const void* image,
                       float* means2D, float* depths, float* conic_opacity,
                       uint32_t* tiles_touched, uint64_t* keys_sorted,
                       uint32_t* ranges, float* final_T, uint32_t* n_contrib)
 {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (P < 0 || W <= 0 || H <= 0) { set_error("bad sizes P=%d W=%d H=%d", P, W, H); return -1; }
+    const Band band{row_begin, row_end};
+    if (int rc = check_band(H, band)) return rc;
     const GeomLayout GL = geom_layout(P);
-    const ImageLayout IL = image_layout(W, H);
+    const ImageLayout IL = image_layout(W, H, band);
     const char* g = static_cast<const char*>(geom);
     const char* im = static_cast<const char*>(image);
-    const uint32_t tiles = (uint32_t)((W + TILE - 1) / TILE) * (uint32_t)((H + TILE - 1) / TILE);
+    const uint32_t grid_x = (uint32_t)((W + TILE - 1) / TILE);
+    const uint32_t tiles = grid_x * (uint32_t)band.rows();
+    const size_t npix = (size_t)W * (size_t)band.height(H);
     if (P > 0 && (means2D || depths || conic_opacity || tiles_touched)) {
         export_geom_kernel<<<(P + 255) / 256, 256, 0, s>>>(
             P, reinterpret_cast<const float4*>(g + GL.splat), reinterpret_cast<const float*>(g + GL.depth),
@@ -284,14 +346,25 @@ EOGS_API int eogs_export_state(eogs_stream_t stream, int P, int W, int H, uint32
         EOGS_LAUNCH_CHECK("export_geom_kernel");
     }
     if (keys_sorted && num_instances > 0) {
-        export_keys_kernel<<<tiles, 128, 0, s>>>(tiles, reinterpret_cast<const uint2*>(im + IL.ranges), point_list,
+        export_keys_kernel<<<tiles, 128, 0, s>>>(tiles, grid_x * (uint32_t)band.row_begin, reinterpret_cast<const uint2*>(im + IL.ranges), point_list,
                                                   reinterpret_cast<const float*>(g + GL.depth), keys_sorted);
         EOGS_LAUNCH_CHECK("export_keys_kernel");
     }
     if (ranges) EOGS_CUDA(cudaMemcpyAsync(ranges, im + IL.ranges, (size_t)tiles * 8, cudaMemcpyDeviceToDevice, s));
-    if (final_T) EOGS_CUDA(cudaMemcpyAsync(final_T, im + IL.final_T, (size_t)W * H * 4, cudaMemcpyDeviceToDevice, s));
-    if (n_contrib) EOGS_CUDA(cudaMemcpyAsync(n_contrib, im + IL.n_contrib, (size_t)W * H * 4, cudaMemcpyDeviceToDevice, s));
+    if (final_T) EOGS_CUDA(cudaMemcpyAsync(final_T, im + IL.final_T, npix * 4, cudaMemcpyDeviceToDevice, s));
+    if (n_contrib) EOGS_CUDA(cudaMemcpyAsync(n_contrib, im + IL.n_contrib, npix * 4, cudaMemcpyDeviceToDevice, s));
     return 0;
+}
+
+EOGS_API int eogs_export_state(eogs_stream_t stream, int P, int W, int H, uint32_t num_instances,
+                      const void* geom, const uint32_t* point_list, const void* image,
+                      float* means2D, float* depths, float* conic_opacity,
+                      uint32_t* tiles_touched, uint64_t* keys_sorted,
+                      uint32_t* ranges, float* final_T, uint32_t* n_contrib)
+{
+    return eogs_export_state_band(stream, P, W, H, 0, (H + TILE - 1) / TILE, num_instances, geom, point_list, image,
+                                  means2D, depths, conic_opacity, tiles_touched, keys_sorted, ranges, final_T,
+                                  n_contrib);
 }
 
 }  // extern "C"

@@ -39,10 +39,22 @@ struct GeomLayout {
 };
 
 struct ImageLayout {
-    size_t final_T;      // float[W*H]
-    size_t n_contrib;    // u32[W*H]
-    size_t ranges;       // uint2[tiles]
+    size_t final_T;      // float[W*band_height]
+    size_t n_contrib;    // u32[W*band_height]
+    size_t ranges;       // uint2[band tiles]
     size_t total;
+};
+
+// A band = the tile rows [row_begin, row_end) of the image that one call renders (multi-GPU
+// tile sharding of one huge view; the whole image is the band [0, grid_y)).  Per-image state
+// (final_T, n_contrib, ranges), the output images and the upstream gradients are band-compact:
+// pixel row y of the image is row y - 16*row_begin of the band buffers, tile (x, y) is entry
+// (y - row_begin) * grid_x + x of `ranges`.
+struct Band {
+    int row_begin, row_end;      // tile rows
+    __host__ __device__ int rows() const { return row_end - row_begin; }
+    __host__ __device__ int y0() const { return row_begin * TILE; }                      // first pixel row
+    __host__ __device__ int height(int H) const { return (row_end * TILE < H ? row_end * TILE : H) - row_begin * TILE; }
 };
 
 struct BinningLayout {
@@ -56,7 +68,9 @@ struct BinningLayout {
 
 size_t sort_temp_bound(size_t n);
 GeomLayout geom_layout(int P);
-ImageLayout image_layout(int W, int H);
+ImageLayout image_layout(int W, int H, Band band);
+Band full_band(int H);
+int check_band(int H, Band band);
 BinningLayout binning_layout(int W, int H, uint32_t I);
 
 // ---- error plumbing ---------------------------------------------------------------------
@@ -86,7 +100,7 @@ void prof_begin(cudaStream_t s);
 void prof_mark(cudaStream_t s, int stage);
 
 // ---- stage launchers (one per .cu) --------------------------------------------------------
-int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, int channels,
+int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int channels,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities, const float* colors,
                           const float* view, float scale_modifier, bool antialiasing,
@@ -95,15 +109,15 @@ int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, int channels,
 int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
                        eogs_forward_info* info_dev);
 
-int launch_binning(cudaStream_t s, int P, int W, int H, uint32_t I, const char* geom,
+int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, const char* geom,
                    const GeomLayout& GL, uint32_t* point_list, char* binning,
                    const BinningLayout& BL, char* image, const ImageLayout& IL);
 
-int launch_blend_fwd(cudaStream_t s, int W, int H, int channels, const char* geom,
+int launch_blend_fwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
                      const GeomLayout& GL, const uint32_t* point_list, char* image,
                      const ImageLayout& IL, const float* bg, float* out_color, float* out_invdepth);
 
-int launch_blend_bwd(cudaStream_t s, int W, int H, int channels, const char* geom,
+int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
                      const GeomLayout& GL, const uint32_t* point_list, const char* image,
                      const ImageLayout& IL, const float* bg, const float* dL_dpix,
                      const float* dL_dinvdepth, float* grad_rec);

@@ -29,7 +29,7 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, float*
 
 template <int C>
 __global__ void __launch_bounds__(PRE_THREADS)
-preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y,
+preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, int band_y1,
                       const float* __restrict__ means3D, const float* __restrict__ scales,
                       const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
                       const float* __restrict__ opacities, const float* __restrict__ colors,
@@ -109,6 +109,10 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y,
         const int x1 = min(grid_x, max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(mx, rf), 16.f), -1.f), 0.0625f))));
         const int y1 = min(grid_y, max(0, __float2int_rz(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(my, rf), 16.f), -1.f), 0.0625f))));
         const uint32_t area = (uint32_t)(x1 - x0) * (uint32_t)(y1 - y0);
+        // Tile sharding: only the rows of this call's band are emitted; radii keep the whole-image
+        // meaning (identical on every rank), tiles / rect are the band's.
+        const int y0b = min(band_y1, max(band_y0, y0)), y1b = min(band_y1, max(band_y0, y1));
+        const uint32_t area_band = (uint32_t)(x1 - x0) * (uint32_t)(y1b - y0b);
 
         if (area != 0u) {
             // depth = 200.0 - altitude; the reference traps when it is negative (forward.cu:267-272).
@@ -118,8 +122,8 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y,
                 atomicOr(&info->error, EOGS_ERR_ALTITUDE_ABOVE_200);
             } else {
                 out_radius = radius;
-                out_tiles = area;
-                out_rect = make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16), (uint32_t)x1 | ((uint32_t)y1 << 16));
+                out_tiles = area_band;
+                out_rect = make_uint2((uint32_t)x0 | ((uint32_t)y0b << 16), (uint32_t)x1 | ((uint32_t)y1b << 16));
                 out_depth = d;
                 out_key = __float_as_uint(d);
                 const float op = __fmul_rn(__ldg(opacities + idx), aa_scale);
@@ -144,7 +148,7 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y,
     rec[0] = r0; rec[1] = r1; rec[2] = r2;
 }
 
-int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, int channels,
+int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int channels,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities, const float* colors,
                           const float* view, float scale_modifier, bool antialiasing,
@@ -157,7 +161,7 @@ int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, int channels,
     if (rotations && !a16(rotations)) { set_error("rotations must be 16-byte aligned"); return -2; }
     auto args = [&](auto kernel) {
         kernel<<<blocks, PRE_THREADS, 0, s>>>(
-            P, W, H, grid_x, grid_y, means3D, scales, reinterpret_cast<const float4*>(rotations),
+            P, W, H, grid_x, grid_y, band.row_begin, band.row_end, means3D, scales, reinterpret_cast<const float4*>(rotations),
             cov3D_precomp, opacities, colors, view, scale_modifier, antialiasing, align_mask, radii,
             reinterpret_cast<float4*>(geom + L.splat), reinterpret_cast<float*>(geom + L.depth),
             reinterpret_cast<uint2*>(geom + L.rect), reinterpret_cast<uint32_t*>(geom + L.tiles),

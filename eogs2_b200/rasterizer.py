@@ -62,6 +62,16 @@ class ForwardState:
     radii: torch.Tensor
     color: Optional[torch.Tensor]
     invdepth: Optional[torch.Tensor]
+    band: Optional[tuple] = None      # (row_begin, row_end) tile rows this state covers; None = whole image
+
+    @property
+    def rows(self) -> tuple:
+        return self.band if self.band is not None else (0, (self.H + 15) // 16)
+
+    @property
+    def band_height(self) -> int:
+        rb, re = self.rows
+        return min(self.H, 16 * re) - 16 * rb
 
 
 _pinned_info: dict = {}
@@ -103,8 +113,11 @@ def _debug_sync(debug: bool, what: str) -> None:
 
 def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, scale_modifier,
                           cov3D_precomp, viewmatrix, image_height, image_width,
-                          antialiasing=False, debug=False) -> ForwardState:
-    """Counterpart of _C.rasterize_gaussians (DGR/rasterize_points.cu:35-124)."""
+                          antialiasing=False, debug=False, band=None) -> ForwardState:
+    """Counterpart of _C.rasterize_gaussians (DGR/rasterize_points.cu:35-124).
+
+    band = (row_begin, row_end): render only those tile rows (multi-GPU tile sharding of one view,
+    eogs2_b200/bands.py); color / invdepth then hold pixel rows [16*row_begin, min(H, 16*row_end))."""
     lib = _cabi.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")       # rasterize_points.cu:58-60
@@ -112,6 +125,11 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         raise _cabi.EogsRasterError("means3D must be a CUDA tensor: this rasterizer has no CPU path")
     dev = means3D.device
     P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    rb, re = (0, (H + 15) // 16) if band is None else (int(band[0]), int(band[1]))
+    if not (0 <= rb < re <= (H + 15) // 16):
+        raise _cabi.EogsRasterError(f"bad band: tile rows [{rb}, {re}) of {(H + 15) // 16}")
+    Hb = min(H, 16 * re) - 16 * rb
+    band = None if band is None else (rb, re)
 
     if colors is None or colors.numel() == 0:
         if P != 0:
@@ -121,14 +139,14 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         channels = int(colors.size(1))
 
     with torch.cuda.device(dev):
-        color = torch.zeros((channels, H, W), dtype=torch.float32, device=dev) if P == 0 else \
-            torch.empty((channels, H, W), dtype=torch.float32, device=dev)
-        invdepth = torch.zeros((1, H, W), dtype=torch.float32, device=dev) if P == 0 else \
-            torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        color = torch.zeros((channels, Hb, W), dtype=torch.float32, device=dev) if P == 0 else \
+            torch.empty((channels, Hb, W), dtype=torch.float32, device=dev)
+        invdepth = torch.zeros((1, Hb, W), dtype=torch.float32, device=dev) if P == 0 else \
+            torch.empty((1, Hb, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         if P == 0:
             # rasterize_points.cu:88 — nothing is launched; the image stays zero (not bg)
-            return ForwardState(0, W, H, channels, 0, None, None, None, radii, color, invdepth)
+            return ForwardState(0, W, H, channels, 0, None, None, None, radii, color, invdepth, band)
 
         means3D = _f32c(means3D, "means3D", dev)
         colors = _f32c(colors, "colors_precomp", dev)
@@ -149,10 +167,10 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         info_dev = geom.data_ptr() + geom_bytes
         info_host = _info_host(dev)
 
-        _cabi.check(lib.eogs_forward_geometry(
-            stream, P, W, H, channels, _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp),
+        _cabi.check(lib.eogs_forward_geometry_band(
+            stream, P, W, H, channels, rb, re, _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp),
             _ptr(opacities), _ptr(colors), _ptr(viewmatrix), float(scale_modifier), int(bool(antialiasing)),
-            radii.data_ptr(), geom.data_ptr(), info_dev, info_host.data_ptr()), "eogs_forward_geometry")
+            radii.data_ptr(), geom.data_ptr(), info_dev, info_host.data_ptr()), "eogs_forward_geometry_band")
         # The instance count sizes the binning buffers (reference: blocking cudaMemcpy,
         # rasterizer_impl.cu:284).
         torch.cuda.current_stream(dev).synchronize()
@@ -163,18 +181,18 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
             raise RuntimeError("Point is too high: a Gaussian's altitude exceeds 200 (depth = 200 - altitude < 0)")
         _debug_sync(debug, "preprocess")
 
-        image = torch.empty(lib.eogs_image_bytes(W, H), dtype=torch.uint8, device=dev)
+        image = torch.empty(lib.eogs_image_bytes_band(W, H, rb, re), dtype=torch.uint8, device=dev)
         point_list = None
         binning = None
         if num_rendered > 0:
             point_list = torch.empty(num_rendered, dtype=torch.int32, device=dev)
             binning = torch.empty(lib.eogs_binning_bytes(W, H, num_rendered), dtype=torch.uint8, device=dev)
-        _cabi.check(lib.eogs_forward_render(
-            stream, P, W, H, channels, num_rendered, geom.data_ptr(), _ptr(point_list), _ptr(binning),
-            image.data_ptr(), _ptr(bg), color.data_ptr(), invdepth.data_ptr()), "eogs_forward_render")
+        _cabi.check(lib.eogs_forward_render_band(
+            stream, P, W, H, channels, rb, re, num_rendered, geom.data_ptr(), _ptr(point_list), _ptr(binning),
+            image.data_ptr(), _ptr(bg), color.data_ptr(), invdepth.data_ptr()), "eogs_forward_render_band")
         _debug_sync(debug, "render")
         del binning   # scratch; the caching allocator keeps it stream-ordered
-    return ForwardState(P, W, H, channels, num_rendered, geom, point_list, image, radii, color, invdepth)
+    return ForwardState(P, W, H, channels, num_rendered, geom, point_list, image, radii, color, invdepth, band)
 
 
 def rasterize_backward_raw(state: ForwardState, bg, means3D, colors, opacities, scales, rotations,
@@ -186,6 +204,7 @@ def rasterize_backward_raw(state: ForwardState, bg, means3D, colors, opacities, 
     lib = _cabi.load()
     dev = means3D.device
     P, W, H, ch = state.P, state.W, state.H, state.channels
+    rb, re = state.rows
     with torch.cuda.device(dev):
         opts = dict(dtype=torch.float32, device=dev)
         dL_dmeans2D = torch.empty((P, 3), **opts)
@@ -211,18 +230,22 @@ def rasterize_backward_raw(state: ForwardState, bg, means3D, colors, opacities, 
         projmatrix = _f32c(projmatrix, "projmatrix", dev)
         bg = _f32c(bg, "bg", dev)
         dL_dcolor = _f32c(dL_dcolor, "grad_out_color", dev)
+        if dL_dcolor.numel() != ch * state.band_height * W:
+            raise RuntimeError(f"grad_out_color has {dL_dcolor.numel()} elements, expected {ch}x{state.band_height}x{W}")
         if dL_dinvdepth is not None:
             dL_dinvdepth = _f32c(dL_dinvdepth, "grad_out_depth", dev)
+            if dL_dinvdepth.numel() != state.band_height * W:
+                raise RuntimeError("grad_out_depth does not match the rendered band")
         grad_scratch = torch.empty(P * 16, **opts)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _cabi.check(lib.eogs_backward(
-            stream, P, W, H, ch, state.num_rendered,
+        _cabi.check(lib.eogs_backward_band(
+            stream, P, W, H, ch, rb, re, state.num_rendered,
             _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp), _ptr(opacities), _ptr(colors),
             _ptr(viewmatrix), _ptr(projmatrix), float(scale_modifier), int(bool(antialiasing)), _ptr(bg),
             state.radii.data_ptr(), state.geom.data_ptr(), _ptr(state.point_list), state.image.data_ptr(),
             _ptr(dL_dcolor), _ptr(dL_dinvdepth), grad_scratch.data_ptr(),
             dL_dmeans2D.data_ptr(), dL_dcolors.data_ptr(), dL_dopacity.data_ptr(), dL_dmeans3D.data_ptr(),
-            _ptr(dL_dcov3D), _ptr(dL_dscales), _ptr(dL_drotations), cam_sums.data_ptr()), "eogs_backward")
+            _ptr(dL_dcov3D), _ptr(dL_dscales), _ptr(dL_drotations), cam_sums.data_ptr()), "eogs_backward_band")
         _debug_sync(debug, "backward")
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales, dL_drotations, cam_sums
 
@@ -248,7 +271,9 @@ def export_state(state: ForwardState) -> dict:
     lib = _cabi.load()
     dev = state.radii.device
     P, W, H, I = state.P, state.W, state.H, state.num_rendered
-    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    rb, re = state.rows
+    tiles = ((W + 15) // 16) * (re - rb)
+    npix = state.band_height * W
     with torch.cuda.device(dev):
         out = {
             "means2D": torch.zeros((P, 2), dtype=torch.float32, device=dev),
@@ -257,16 +282,16 @@ def export_state(state: ForwardState) -> dict:
             "tiles_touched": torch.zeros((P,), dtype=torch.int32, device=dev),
             "keys_sorted": torch.zeros((I,), dtype=torch.int64, device=dev),
             "ranges": torch.zeros((tiles, 2), dtype=torch.int32, device=dev),
-            "final_T": torch.zeros((H * W,), dtype=torch.float32, device=dev),
-            "n_contrib": torch.zeros((H * W,), dtype=torch.int32, device=dev),
+            "final_T": torch.zeros((npix,), dtype=torch.float32, device=dev),
+            "n_contrib": torch.zeros((npix,), dtype=torch.int32, device=dev),
         }
         if P > 0:
             stream = torch.cuda.current_stream(dev).cuda_stream
-            _cabi.check(lib.eogs_export_state(
-                stream, P, W, H, I, state.geom.data_ptr(), _ptr(state.point_list), state.image.data_ptr(),
+            _cabi.check(lib.eogs_export_state_band(
+                stream, P, W, H, rb, re, I, state.geom.data_ptr(), _ptr(state.point_list), state.image.data_ptr(),
                 out["means2D"].data_ptr(), out["depths"].data_ptr(), out["conic_opacity"].data_ptr(),
                 out["tiles_touched"].data_ptr(), _ptr(out["keys_sorted"]), out["ranges"].data_ptr(),
-                out["final_T"].data_ptr(), out["n_contrib"].data_ptr()), "eogs_export_state")
+                out["final_T"].data_ptr(), out["n_contrib"].data_ptr()), "eogs_export_state_band")
         out["point_list"] = state.point_list if state.point_list is not None else \
             torch.zeros((0,), dtype=torch.int32, device=dev)
         out["radii"] = state.radii
@@ -297,7 +322,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         # color.grad_fn is this node, so ctx -> state -> color would be a reference cycle that only
         # Python's cyclic GC frees, and every step would then cudaMalloc fresh buffers.
         ctx.state = ForwardState(state.P, state.W, state.H, state.channels, state.num_rendered,
-                                 state.geom, state.point_list, state.image, state.radii, None, None)
+                                 state.geom, state.point_list, state.image, state.radii, None, None, state.band)
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, opacities)
         ctx.mark_non_differentiable(state.radii)
         # An unused output (EOGS never reads invdepths) then arrives as None in backward instead of a

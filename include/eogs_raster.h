@@ -51,7 +51,7 @@ extern "C" {
 #define EOGS_API
 #endif
 
-#define EOGS_ABI_VERSION 1
+#define EOGS_ABI_VERSION 2
 #define EOGS_TILE 16            /* BLOCK_X = BLOCK_Y = 16, DGR/cuda_rasterizer/config.h:15-16 */
 #define EOGS_MAX_CHANNELS 5     /* NUM_CHANNELS 5,        DGR/cuda_rasterizer/config.h:14    */
 
@@ -159,6 +159,47 @@ EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channe
                   float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
                   float* dL_drotations, float* cam_sums);
 
+/* ---- tile-band variants (multi-GPU sharding of ONE view) ---------------------------- */
+/* Not in the reference (it has no multi-device code): tiles are independent
+ * after binning, so a huge view (BASELINE configs[4]: 8192^2) is split into horizontal bands of
+ * tile rows [row_begin, row_end), one band per GPU.  Each *_band call behaves like its
+ * whole-image counterpart restricted to the band's tiles:
+ *   - every Gaussian is projected (radii keep the whole-image meaning, identical on every rank);
+ *     only the (Gaussian, tile) instances inside the band are emitted, sorted and blended, so
+ *     the band's sorted list and ranges equal the whole-image ones restricted to those tiles
+ *     (list offsets shifted by the band's base);
+ *   - per-image buffers are band-compact: `image` has eogs_image_bytes_band() bytes, and
+ *     out_color [channels, band_h, W], out_invdepth [band_h, W], dL_dpix [channels, band_h, W],
+ *     dL_dinvdepth [band_h, W] hold pixel rows [16*row_begin, min(H, 16*row_end)) only;
+ *   - eogs_backward_band returns the band's share of every gradient and of cam_sums; the
+ *     whole-image gradient is the sum over bands (an NCCL all-reduce across ranks).
+ * The whole-image entry points above are the band [0, ceil(H/16)). */
+EOGS_API size_t eogs_image_bytes_band(int W, int H, int row_begin, int row_end);
+EOGS_API int eogs_forward_geometry_band(eogs_stream_t stream, int P, int W, int H, int channels,
+                          int row_begin, int row_end,
+                          const float* means3D, const float* scales, const float* rotations,
+                          const float* cov3D_precomp, const float* opacities, const float* colors,
+                          const float* viewmatrix, float scale_modifier, int antialiasing,
+                          int32_t* radii, void* geom, eogs_forward_info* info_dev,
+                          eogs_forward_info* info_host);
+EOGS_API int eogs_forward_render_band(eogs_stream_t stream, int P, int W, int H, int channels,
+                        int row_begin, int row_end,
+                        uint32_t num_instances, const void* geom, uint32_t* point_list,
+                        void* binning, void* image, const float* bg,
+                        float* out_color, float* out_invdepth);
+EOGS_API int eogs_backward_band(eogs_stream_t stream, int P, int W, int H, int channels,
+                  int row_begin, int row_end, uint32_t num_instances,
+                  const float* means3D, const float* scales, const float* rotations,
+                  const float* cov3D_precomp, const float* opacities, const float* colors,
+                  const float* viewmatrix, const float* projmatrix,
+                  float scale_modifier, int antialiasing, const float* bg,
+                  const int32_t* radii, const void* geom, const uint32_t* point_list,
+                  const void* image, const float* dL_dpix, const float* dL_dinvdepth,
+                  float* grad_scratch,
+                  float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                  float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                  float* dL_drotations, float* cam_sums);
+
 /* ---- markVisible ------------------------------------------------------------------- */
 /* The reference's in_frustum culls nothing for affine cameras (its body is
  * commented out, auxiliary.h:151-176): every Gaussian is reported visible. */
@@ -182,6 +223,15 @@ EOGS_API int eogs_profile_read(float* ms, int n);
  *   keys_sorted [I] u64 = (tile << 32) | depth bits, rebuilt from point_list
  *   ranges [tiles,2] u32, final_T [H*W], n_contrib [H*W] u32 : imgState fields */
 EOGS_API int eogs_export_state(eogs_stream_t stream, int P, int W, int H, uint32_t num_instances,
+                      const void* geom, const uint32_t* point_list, const void* image,
+                      float* means2D, float* depths, float* conic_opacity,
+                      uint32_t* tiles_touched, uint64_t* keys_sorted,
+                      uint32_t* ranges, float* final_T, uint32_t* n_contrib);
+
+/* Band variant: tiles_touched counts the band's tiles, keys_sorted carry whole-image tile ids,
+ * ranges [band tiles,2], final_T / n_contrib [band_h*W]. */
+EOGS_API int eogs_export_state_band(eogs_stream_t stream, int P, int W, int H, int row_begin, int row_end,
+                      uint32_t num_instances,
                       const void* geom, const uint32_t* point_list, const void* image,
                       float* means2D, float* depths, float* conic_opacity,
                       uint32_t* tiles_touched, uint64_t* keys_sorted,

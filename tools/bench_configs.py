@@ -1,0 +1,210 @@
+"""All five BASELINE.json configs on the GPU box, ours next to the compiled reference (oracle/_ref).
+
+    python tools/bench_configs.py [--configs 1,2,3,5] [--reps 5] [--out gpurun_out/<tag>/configs.json]
+    python -m torch.distributed.run --nproc-per-node N ... tools/bench_configs.py --configs 5     (tile bands over N GPUs)
+
+bench.py stays the one headline line (configs[2] main view); this script produces the table quoted in
+DESIGN.md / profiles/: device time per config (CUDA events, median of --reps after 2 warm-ups, L2
+flushed between reps), instances, and the same workload through the reference's own kernels.
+  1  50 k Gaussians, 512^2, fwd+bwd                                     (configs[0])
+  2  300 k Gaussians, 19 views 2048^2, one training iteration = 19 fwd+bwd   (configs[1])
+  3  1 M Gaussians: main 2048^2 + sun 4096^2 + random 2048^2, fwd+bwd, camera gradients (configs[2])
+  5  5 M Gaussians, 8192^2 forward (altitude/DSM), tile bands: 1 GPU = whole image; N GPUs = N bands
+     + all-gather                                                        (configs[4])
+(config 4 = config 3's cameras data-parallel over ranks is what `bench.py --gpus N` measures.)
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import eogs2_b200 as E                      # noqa: E402
+from eogs2_b200 import bands as B           # noqa: E402
+from eogs2_b200 import scene as S           # noqa: E402
+from oracle import ref_rasterizer as R      # noqa: E402
+
+
+def timed(fn, reps, flush, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    return statistics.median(ts)
+
+
+class Views:
+    def __init__(self, dev, P, kind, seed):
+        self.dev = dev
+        self.sc = S.make_scene(P, kind, seed)
+        self.d = {k: getattr(self.sc, k).to(dev) for k in ("means3D", "scales", "rotations", "opacities")}
+        self.empty = torch.empty(0, device=dev)
+        self.campos = torch.zeros(3, device=dev)
+        self.bg = S.background(seed).to(dev)
+
+    def view(self, view, W, H, seed):
+        dcol, dinv = S.upstream_grads(5, H, W, seed, False)
+        return dict(view=view.to(self.dev), colors=S.colors_precomp(self.sc, view).to(self.dev), W=W, H=H,
+                    dcol=dcol.to(self.dev), dinv=dinv.to(self.dev))
+
+    def ours(self, v, backward=True, band=None):
+        d = self.d
+        st = E.rasterize_forward_raw(self.bg, d["means3D"], v["colors"], d["opacities"], d["scales"], d["rotations"],
+                                     1.0, self.empty, v["view"], v["H"], v["W"], False, False, band=band)
+        if backward:
+            E.rasterize_backward_raw(st, self.bg, d["means3D"], v["colors"], d["opacities"], d["scales"],
+                                     d["rotations"], 1.0, self.empty, v["view"], v["view"], v["dcol"], v["dinv"])
+        return st
+
+    def ref(self, v, backward=True):
+        d = self.d
+        st = R.forward(self.bg, d["means3D"], v["colors"], d["opacities"], d["scales"], d["rotations"], 1.0,
+                       self.empty, v["view"], v["view"], 1.0, 1.0, v["H"], v["W"], self.campos, False, False)
+        if backward:
+            R.backward(st, self.bg, d["means3D"], v["colors"], d["opacities"], d["scales"], d["rotations"], 1.0,
+                       self.empty, v["view"], v["view"], 1.0, 1.0, v["dcol"], v["dinv"], self.campos, False)
+        return st
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="1,2,3,5")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--p5", type=int, default=5_000_000)
+    ap.add_argument("--img5", type=int, default=8192)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    have_ref = R.available() and not args.no_ref
+    rows = []
+    want = [int(x) for x in args.configs.split(",")]
+
+    def report(name, ms_ours, ms_ref, extra):
+        row = dict(config=name, ours_ms=round(ms_ours, 4), ref_ms=None if ms_ref is None else round(ms_ref, 4),
+                   speedup=None if ms_ref is None else round(ms_ref / ms_ours, 2), **extra)
+        rows.append(row)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+
+    if 1 in want and world == 1:
+        for kind in ("trained", "init"):
+            V = Views(dev, 50_000, kind, 1337)
+            v = V.view(S.make_camera(1337), 512, 512, 1337)
+            st = V.ours(v)
+            report(f"1: 50k {kind}, 512^2 fwd+bwd", timed(lambda: V.ours(v), args.reps, flush),
+                   timed(lambda: V.ref(v), args.reps, flush) if have_ref else None, dict(instances=st.num_rendered))
+
+    if 2 in want and world == 1:
+        V = Views(dev, 300_000, "trained", 1337)
+        views = [V.view(S.make_camera(1337 + i), 2048, 2048, 1337 + i) for i in range(19)]
+        inst = sum(V.ours(v, backward=False).num_rendered for v in views)
+        report("2: 300k, 19 views 2048^2, one iteration (19 fwd+bwd)",
+               timed(lambda: [V.ours(v) for v in views], args.reps, flush),
+               timed(lambda: [V.ref(v) for v in views], args.reps, flush) if have_ref else None,
+               dict(instances=inst))
+        del views
+
+    if 3 in want and world == 1:
+        V = Views(dev, 1_000_000, "trained", 1337)
+        cam = S.make_camera(1337)
+        trio = [V.view(cam, 2048, 2048, 1), V.view(S.sun_camera(cam), 4096, 4096, 2),
+                V.view(S.random_camera(cam, 0.01, 3), 2048, 2048, 3)]
+        inst = [V.ours(v, backward=False).num_rendered for v in trio]
+        for nm, v in zip(("main 2048^2", "sun 4096^2", "random 2048^2"), trio):
+            report(f"3: 1M, {nm} fwd+bwd", timed(lambda: V.ours(v), args.reps, flush),
+                   timed(lambda: V.ref(v), args.reps, flush) if have_ref else None,
+                   dict(instances=V.ours(v, backward=False).num_rendered))
+        report("3: 1M, iteration = main + sun@2x + random, fwd+bwd",
+               timed(lambda: [V.ours(v) for v in trio], args.reps, flush),
+               timed(lambda: [V.ref(v) for v in trio], args.reps, flush) if have_ref else None,
+               dict(instances=sum(inst)))
+        del trio
+
+    if 5 in want:
+        P5, IMG5 = args.p5, args.img5
+        V = Views(dev, P5, "trained", 1337)
+        A = torch.tensor([[1 / 0.72, 0, 0], [0, 1 / 0.72, 0], [0, 0, S.METRES_PER_UNIT]])      # nadir camera
+        v = V.view(S.affine_to_viewmatrix(A, torch.zeros(3)), IMG5, IMG5, 5)
+        grid_y = (IMG5 + 15) // 16
+        if world == 1:
+            st = V.ours(v, backward=False)
+            inst = st.num_rendered
+            del st
+            ms_ref = None
+            if have_ref:
+                try:
+                    ms_ref = timed(lambda: V.ref(v, backward=False), max(2, args.reps // 2), flush, warm=1)
+                except Exception as ex:                       # reference may exceed its 32-bit / memory limits
+                    print("reference failed on config 5:", str(ex)[:200], file=sys.stderr)
+            report(f"5: {P5/1e6:g}M, {IMG5}^2 forward (altitude/DSM), 1 GPU whole image",
+                   timed(lambda: V.ours(v, backward=False), args.reps, flush), ms_ref, dict(instances=inst))
+            # the same image as 8 bands rendered one after the other on this GPU (sharding overhead)
+            bands = B.split_rows(grid_y, 8)
+            report(f"5: same, 8 bands sequentially on 1 GPU",
+                   timed(lambda: [V.ours(v, backward=False, band=b) for b in bands], args.reps, flush), None,
+                   dict(instances=inst))
+        else:
+            import torch.distributed as dist
+            d = V.d
+
+            def step(weights=None):
+                return B.forward_band(V.bg, d["means3D"], v["colors"], d["opacities"], d["scales"], d["rotations"],
+                                      1.0, V.empty, v["view"], IMG5, IMG5, rank, world, weights=weights)
+            color, invd, st = step()
+            # balanced bands from the per-row instance counts of this (static) view: every rank counts its rows
+            ex = E.export_state(st)
+            r = ex["ranges"].to(torch.int64)
+            per_row = (r[:, 1] - r[:, 0]).view(-1, (IMG5 + 15) // 16).sum(1)
+            all_rows = torch.zeros(grid_y, dtype=torch.int64, device=dev)
+            all_rows[st.rows[0]:st.rows[1]] = per_row
+            dist.all_reduce(all_rows)
+            weights = all_rows.cpu().tolist()
+            for nm, w in (("even rows", None), ("instance-balanced rows", weights)):
+                for _ in range(2):
+                    step(w)
+                ts = []
+                for _ in range(args.reps):
+                    flush.fill_(1)
+                    torch.cuda.synchronize(); dist.barrier()
+                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    s.record(); step(w); e.record()
+                    torch.cuda.synchronize()
+                    t = torch.tensor([s.elapsed_time(e)], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ts.append(float(t.item()))
+                report(f"5: {P5/1e6:g}M, {IMG5}^2 forward, {world} GPUs = {world} tile bands + all-gather, {nm}",
+                       statistics.median(ts), None, dict(instances=int(all_rows.sum().item()), max_over_ranks=True))
+            # checksum so runs at different N can be compared: the gathered image must not depend on N
+            if rank == 0:
+                print(json.dumps({"config5_checksum": float(color.double().sum().item()),
+                                  "alt_checksum": float(color[3].double().abs().sum().item())}), flush=True)
+
+    if args.out and rank == 0:
+        Path(args.out).parent.mkdir(parents=True, exist_ok=True)
+        Path(args.out).write_text(json.dumps(rows, indent=1))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
