@@ -10,7 +10,8 @@ import ctypes as C
 import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libeogs_raster.so"
+# EOGS_RASTER_LIB selects another build of the SAME library (developer A/B runs, eogs2_b200/build.py)
+LIB_PATH = Path(os.environ.get("EOGS_RASTER_LIB") or Path(__file__).resolve().parent / "libeogs_raster.so")
 
 c_f32p = C.c_void_p      # device pointers travel as integers (tensor.data_ptr())
 c_ptr = C.c_void_p

@@ -20,8 +20,12 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
-BUILD = PKG_DIR / "csrc" / "build"
-LIB = PKG_DIR / "libeogs_raster.so"
+# Developer A/B builds: EOGS_NVCC_DEFS="-DX=1 -DY=2" EOGS_LIB_SUFFIX=_x builds libeogs_raster_x.so next to the
+# product library (objects under csrc/build_x/); select it at run time with EOGS_RASTER_LIB=<path>.
+_SUFFIX = os.environ.get("EOGS_LIB_SUFFIX", "")
+_EXTRA_DEFS = os.environ.get("EOGS_NVCC_DEFS", "").split()
+LIB = PKG_DIR / f"libeogs_raster{_SUFFIX}.so"
+BUILD = PKG_DIR / "csrc" / f"build{_SUFFIX}"
 SOURCES = ["cabi.cu", "preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
@@ -45,7 +49,7 @@ def _compile(src: str, nvcc: str, force: bool, log: list) -> Path:
     o = BUILD / (src.replace(".cu", ".o"))
     if not force and o.exists() and o.stat().st_mtime > max(s.stat().st_mtime, _deps_mtime()):
         return o
-    cmd = [nvcc, *NVCC_FLAGS, "-c", str(s), "-o", str(o)]
+    cmd = [nvcc, *NVCC_FLAGS, *_EXTRA_DEFS, "-c", str(s), "-o", str(o)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log.append((src, r.stderr))
     if r.returncode != 0:

@@ -35,18 +35,32 @@
 // Bound: FP32 issue.  Algorithmic HBM bytes: 4 B id + 48 B record gathered per instance up to the
 // tile's max(n_contrib), 44 B reduced per surviving (tile, Gaussian), 4*(C+1) + 8 B per pixel in.
 #include "blend_common.cuh"
+#include "f32x2.cuh"
 
 namespace eogs {
 
 constexpr int BWD_WARPS = 4;                 // tiles per CTA: a 2x2 block of tiles
 constexpr int BWD_THREADS = BWD_WARPS * 32;
 constexpr int NPATCH = (TILE / PATCH_W) * (TILE / PATCH_H);   // 8
+constexpr int NSTRIP = NPATCH / 2;           // 4 strips of 16x4 pixels = a left and a right patch
 
+// Tuning switches (A/B measured on B200): where the per-pixel dynamic state lives.
+#ifndef EOGS_BWD_STATE_SMEM
+#define EOGS_BWD_STATE_SMEM 0                // 1: T / accum in shared memory (-16 registers, +2 LDS/STS per strip)
+#endif
+
+// Per-pixel constants of a lane's pixel PAIR in strip r (left patch 2r, right patch 2r+1), laid out
+// as the f32x2 operands the replay consumes: an LDS.128 lands two ready-made register pairs.
 struct BwdWarpSmem {
-    float4 rec[2][REC_F4][32];        // two stages of 32 packed records
-    float4 pix_a[NPATCH][32];         // dL_dpixel[0..3]           of pixel (patch, lane)
-    float4 pix_b[NPATCH][32];         // dL_dpixel[4], dL_dinvdepth, T_final * (bg . dL_dpixel), -
-};
+    float4 rec[2][32][REC_F4];        // two stages of 32 packed records (cp.async destinations, 48 B each)
+    uint32_t rid[2][32];              // Gaussian id of each staged record
+    float4 pix[NSTRIP][4][32];        // [0] = {g0.L, g0.R, g1.L, g1.R}   [1] = {g2.L, g2.R, g3.L, g3.R}
+                                      // [2] = {g4.L, g4.R, ginv.L, ginv.R}
+                                      // [3] = {-T_final (bg . g).L, same .R, n_contrib.L, n_contrib.R (int bits)}
+#if EOGS_BWD_STATE_SMEM
+    float4 state[NSTRIP][32];         // dynamic per-pixel-pair state {T.L, T.R, accum.L, accum.R}
+#endif
+};                                    // g = dL_dpixel
 
 // 4 CTAs (16 warps) per SM measured best: 3 (142 regs) and 5 (96 regs) are both 14 % slower.
 template <int C>
@@ -60,7 +74,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 {
     constexpr int NV = 6 + C;   // mean2D.xy, conic.xyw, opacity, colours
     constexpr uint32_t FULL = 0xffffffffu;
-    __shared__ BwdWarpSmem s_warp[BWD_WARPS];
+    extern __shared__ __align__(16) unsigned char s_dyn[];       // BWD_WARPS x BwdWarpSmem (> 48 KB: opt-in)
+    BwdWarpSmem* s_warp = reinterpret_cast<BwdWarpSmem*>(s_dyn);
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     // tiles_y = tile rows of the band; brow = row inside the band, tile_y = row in the image
@@ -75,75 +90,98 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const uint32_t* list = point_list + range.x;
 
     // ---- per-pixel state: pixel (patch p, lane) = (tile_x*16 + 8*(p&1) + (lane&7), tile_y*16 + 4*(p>>1) + (lane>>3))
-    float pxf[2], pyf[4];
-    pxf[0] = tx0 + (float)(lane & 7u); pxf[1] = pxf[0] + (float)PATCH_W;
-#pragma unroll
-    for (int r = 0; r < 4; r++) pyf[r] = ty0 + (float)(PATCH_H * r) + (float)(lane >> 3);
+    const float pxl = tx0 + (float)(lane & 7u);
+    const f2 neg_px = mk2(-pxl, -(pxl + (float)PATCH_W));       // dx = mean.x - px as an add
+    const float py_lane = ty0 + (float)(lane >> 3);              // + 4r = the strip's pixel row (exact)
 
     float bgv[C];
 #pragma unroll
     for (int ch = 0; ch < C; ch++) bgv[ch] = __ldg(bg + ch);
 
-    int ncon[NPATCH], pmax[NPATCH];
-    float T[NPATCH], accum[NPATCH];
+    int pmax[NPATCH], ncon[NPATCH];
+#if !EOGS_BWD_STATE_SMEM
+    f2 T2[NSTRIP], accum2[NSTRIP];
+#endif
     int nmax = 0;
 #pragma unroll
-    for (int p = 0; p < NPATCH; p++) {
-        const int px = tile_x * TILE + PATCH_W * (p & 1) + (int)(lane & 7u);
-        const int py = tile_y * TILE + PATCH_H * (p >> 1) + (int)(lane >> 3);
-        const bool inside = px < W && py < H;
-        const size_t pix_id = (size_t)(py - band_row0 * TILE) * W + px;     // band-compact buffers
-        ncon[p] = inside ? (int)__ldg(n_contrib + pix_id) : 0;
-        const float Tf = inside ? __ldg(final_T + pix_id) : 0.f;
-        T[p] = Tf;
-        accum[p] = 0.f;
-        float g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        float bg_dot_g = 0.f;
+    for (int r = 0; r < NSTRIP; r++) {
+        float g[2][5], g_inv[2], Tf[2], nbg[2];
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) {
-            g[ch] = inside ? __ldg(dL_dpix + (size_t)ch * band_h * W + pix_id) : 0.f;
-            bg_dot_g = fmaf(bgv[ch], g[ch], bg_dot_g);
+        for (int h = 0; h < 2; h++) {
+            const int p = 2 * r + h;
+            const int px = tile_x * TILE + PATCH_W * h + (int)(lane & 7u);
+            const int py = tile_y * TILE + PATCH_H * r + (int)(lane >> 3);
+            const bool inside = px < W && py < H;
+            const size_t pix_id = (size_t)(py - band_row0 * TILE) * W + px;     // band-compact buffers
+            ncon[p] = inside ? (int)__ldg(n_contrib + pix_id) : 0;
+            Tf[h] = inside ? __ldg(final_T + pix_id) : 0.f;
+            float bg_dot_g = 0.f;
+#pragma unroll
+            for (int ch = 0; ch < 5; ch++) {
+                g[h][ch] = (ch < C && inside) ? __ldg(dL_dpix + (size_t)ch * band_h * W + pix_id) : 0.f;
+                if (ch < C) bg_dot_g = fmaf(bgv[ch], g[h][ch], bg_dot_g);
+            }
+            g_inv[h] = (inside && dL_dinvdepth) ? __ldg(dL_dinvdepth + pix_id) : 0.f;
+            nbg[h] = -Tf[h] * bg_dot_g;
+            pmax[p] = __reduce_max_sync(FULL, ncon[p]);
+            nmax = max(nmax, pmax[p]);
         }
-        const float g_inv = (inside && dL_dinvdepth) ? __ldg(dL_dinvdepth + pix_id) : 0.f;
-        sm.pix_a[p][lane] = make_float4(g[0], g[1], g[2], g[3]);
-        sm.pix_b[p][lane] = make_float4(g[4], g_inv, Tf * bg_dot_g, 0.f);
-        pmax[p] = __reduce_max_sync(FULL, ncon[p]);
-        nmax = max(nmax, pmax[p]);
+        sm.pix[r][0][lane] = make_float4(g[0][0], g[1][0], g[0][1], g[1][1]);
+        sm.pix[r][1][lane] = make_float4(g[0][2], g[1][2], g[0][3], g[1][3]);
+        sm.pix[r][2][lane] = make_float4(g[0][4], g[1][4], g_inv[0], g_inv[1]);
+        sm.pix[r][3][lane] = make_float4(nbg[0], nbg[1], 0.f, 0.f);
+#if EOGS_BWD_STATE_SMEM
+        sm.state[r][lane] = make_float4(Tf[0], Tf[1], 0.f, 0.f);
+#else
+        T2[r] = mk2(Tf[0], Tf[1]);
+        accum2[r] = bc2(0.f);
+#endif
     }
     if (nmax == 0) return;                     // entries [nmax, n) were blended by no pixel of this tile
     const int rounds = (nmax + 31) >> 5;
 
-    // Batch b, lane l holds list position nmax-1 - (32 b + l): back to front.
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-    uint32_t rid = 0, id_next = 0;
+    // Batch b, lane l holds list position nmax-1 - (32 b + l): back to front.  Records travel
+    // global -> shared with cp.async (no staging registers), one batch ahead of the replay.
+    uint32_t id_next = 0;
     {
         const int p0 = nmax - 1 - (int)lane;
-        if (p0 >= 0) { rid = __ldg(list + p0); fetch_record(splat, rid, r0, r1, r2); }
+        if (p0 >= 0) {
+            const uint32_t id = __ldg(list + p0);
+            sm.rid[0][lane] = id;
+            const float4* src = splat + (size_t)id * REC_F4;
+#pragma unroll
+            for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[0][lane][k], src + k);
+        }
+        cp_async_commit();
         if (p0 - 32 >= 0) id_next = __ldg(list + p0 - 32);
     }
     const int my_slot = fold_slot<NV>(lane);
-    // the butterfly leaves the mean2D sums un-scaled: d(pixel)/d(ndc) is applied once per flush
-    const float slot_scale = my_slot == 0 ? 0.5f * (float)W : (my_slot == 1 ? 0.5f * (float)H : 1.f);
+    // The accumulators are kept un-scaled and un-signed; the constant factors of each gradient slot
+    // are applied once per flush: mean2D gets -d(pixel)/d(ndc), the conic terms -1/2.
+    const float slot_scale = my_slot == 0 ? -0.5f * (float)W : my_slot == 1 ? -0.5f * (float)H :
+                             (my_slot >= 2 && my_slot <= 4) ? -0.5f : 1.f;
 
     int first = nmax - 1;                      // list position held by lane 0 in this batch
     for (int i = 0; i < rounds; i++, first -= 32) {
         const int pos = first - (int)lane;
-        uint32_t m = pos >= 0 ? patch_mask(r0, r1, tx0, ty0, img_x1, img_y1) : 0u;
+        const int stage = i & 1;
+        cp_async_wait<0>();                    // this lane's record of batch i has landed
+        uint32_t m = 0u;
+        if (pos >= 0) m = patch_mask(sm.rec[stage][lane][0], sm.rec[stage][lane][1], tx0, ty0, img_x1, img_y1);
 #pragma unroll
         for (int p = 0; p < NPATCH; p++)
             if (pos >= pmax[p]) m &= ~(1u << p);               // every pixel of patch p stopped before pos
-        const int stage = i & 1;
-        if (m) {
-            sm.rec[stage][0][lane] = r0;
-            sm.rec[stage][1][lane] = r1;
-            sm.rec[stage][2][lane] = r2;
-        }
-        const uint32_t cur_rid = rid;
         uint32_t todo = __ballot_sync(FULL, m != 0u);
-        __syncwarp();
+        __syncwarp();                          // all lanes' records visible; previous batch's stage is free
 
         // next batch's records are in flight while this one is replayed
-        if (pos - 32 >= 0) { rid = id_next; fetch_record(splat, rid, r0, r1, r2); }
+        if (pos - 32 >= 0) {
+            sm.rid[stage ^ 1][lane] = id_next;
+            const float4* src = splat + (size_t)id_next * REC_F4;
+#pragma unroll
+            for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[stage ^ 1][lane][k], src + k);
+        }
+        cp_async_commit();
         if (pos - 64 >= 0) id_next = __ldg(list + pos - 64);
 
         while (todo) {
@@ -151,80 +189,104 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             todo &= todo - 1u;
             const uint32_t me = __shfl_sync(FULL, m, e);
             const int pos_e = first - e;
-            const float4 ra = sm.rec[stage][0][e];
-            const float4 rb = sm.rec[stage][1][e];
-            const float4 rc = sm.rec[stage][2][e];
+            const float4 ra = sm.rec[stage][e][0];     // mean.x, mean.y, conic.x, conic.y
+            const float4 rb = sm.rec[stage][e][1];     // conic.z, opacity, c0, c1
+            const float4 rc = sm.rec[stage][e][2];     // c2, c3, c4, 1/depth
             const float col[5] = {rb.z, rb.w, rc.x, rc.y, rc.z};
 
-            float v[NV];
+            f2 v2[NV];
 #pragma unroll
-            for (int k = 0; k < NV; k++) v[k] = 0.f;
-            bool any = false;
+            for (int k = 0; k < NV; k++) v2[k] = bc2(0.f);
+            bool any;
 
-            // Two patches (the left and right half of one 4-pixel-high band) per step: two independent
-            // dependency chains per lane, written branch-free — a rejected pixel runs the same
-            // arithmetic with alpha = G = dL_dalpha = 0, which leaves T, accum and every accumulator
-            // unchanged.  A patch whose mask bit is clear cannot be accepted (the mask is conservative),
-            // so the bits only decide whether the band is visited at all.
+            // the forward's exponent in its op order (pair_power), on the lane's (left, right) pixel pair
+            const f2 dx2 = add2(bc2(ra.x), neg_px);
+            const f2 zdx2 = mul2(bc2(ra.z), dx2);
+            const f2 wdx2 = mul2(bc2(ra.w), dx2);
+
+            // One 16x4 strip per step = one pixel PAIR per lane, all arithmetic packed (FFMA2).  Written
+            // branch-free: a rejected pixel runs the same arithmetic with alpha = G = 0, which leaves T,
+            // accum and every accumulator unchanged.  A patch whose mask bit is clear cannot be accepted
+            // (the mask is conservative), so the bits only decide whether the strip is visited at all.
+            // Stage A, all four strips up front and branch-free: G, alpha and the accept test of the lane's
+            // 8 pixels depend only on geometry, never on the replay state, so the four chains
+            // (FFMA2 -> ex2 -> min -> compare) are independent and overlap each other's latency.
+            f2 a2[NSTRIP], Gv2[NSTRIP];
+            uint32_t live = 0u;                                   // bit r: some pixel of strip r accepts this entry
 #pragma unroll
-            for (int r = 0; r < NPATCH / 2; r++) {
-                if (!((me >> (2 * r)) & 3u)) continue;           // warp-uniform
-                const float dy = __fsub_rn(ra.y, pyf[r]);
+            for (int r = 0; r < NSTRIP; r++) {
+                const float dy = __fsub_rn(ra.y, py_lane + (float)(PATCH_H * r));
                 const float cyy = __fmul_rn(__fmul_rn(rb.x, dy), dy);
-                float dx[2], G[2], alpha[2];
-                bool valid[2];
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    // the forward's exponent, same op order (pair_power); exp through ex2.approx:
-                    // gradients carry a 1e-3 bar, not the forward's bit-exact one
-                    dx[h] = __fsub_rn(ra.x, pxf[h]);
-                    const float quad = __fmaf_rn(dx[h], __fmul_rn(ra.z, dx[h]), cyy);
-                    const float power = __fmaf_rn(quad, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx[h]), dy));
-                    G[h] = fast_exp(power);
-                    alpha[h] = fminf(0.99f, rb.y * G[h]);
-                    // Entry at list position pos_e is blended by a pixel iff pos_e < n_contrib (backward.cu:556-558).
-                    valid[h] = pos_e < ncon[2 * r + h] && !(power > 0.0f) && !(alpha[h] < 1.0f / 255.0f);
-                }
-                if (!__any_sync(FULL, valid[0] || valid[1])) continue;
-                any = true;
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int p = 2 * r + h;
-                    const float4 ga = sm.pix_a[p][lane];
-                    const float4 gb = sm.pix_b[p][lane];
-                    const float g[5] = {ga.x, ga.y, ga.z, ga.w, gb.x};
-                    const float a = valid[h] ? alpha[h] : 0.f;
-                    const float Gv = valid[h] ? G[h] : 0.f;
-                    const float inv_1ma = fast_rcp(1.f - a);          // exactly 1 for a rejected pixel
-                    const float Tn = T[p] * inv_1ma;
-                    T[p] = Tn;
-                    const float w = a * Tn;
-                    float cg = rc.w * gb.y;
-#pragma unroll
-                    for (int ch = 0; ch < C; ch++) {
-                        v[6 + ch] = fmaf(w, g[ch], v[6 + ch]);
-                        cg = fmaf(col[ch], g[ch], cg);
-                    }
-                    // accum = (colour blended behind this entry) . dL_dpixel
-                    const float behind = cg - accum[p];
-                    const float dL_dalpha = valid[h] ? fmaf(-gb.z, inv_1ma, behind * Tn) : 0.f;
-                    accum[p] = fmaf(a, behind, accum[p]);
+                const f2 quad2 = fma2(dx2, zdx2, bc2(cyy));
+                const f2 power2 = fma2(quad2, bc2(-0.5f), mul2(wdx2, bc2(-dy)));
+                // exp through ex2.approx: gradients carry a 1e-3 bar, not the forward's bit-exact one
+                const f2 pl2 = mul2(power2, bc2(1.4426950408889634f));
+                const float G0 = ex2_approx(lo2(pl2)), G1 = ex2_approx(hi2(pl2));
+                const f2 og2 = mul2(bc2(rb.y), mk2(G0, G1));
+                const float al0 = fminf(0.99f, lo2(og2)), al1 = fminf(0.99f, hi2(og2));
+                // entry at list position pos_e is blended by a pixel iff pos_e < n_contrib (backward.cu:556-558)
+                const bool v0 = pos_e < ncon[2 * r] && !(lo2(power2) > 0.0f) && !(al0 < 1.0f / 255.0f);
+                const bool v1 = pos_e < ncon[2 * r + 1] && !(hi2(power2) > 0.0f) && !(al1 < 1.0f / 255.0f);
+                a2[r] = mk2(v0 ? al0 : 0.f, v1 ? al1 : 0.f);
+                Gv2[r] = mk2(v0 ? G0 : 0.f, v1 ? G1 : 0.f);
+                if (__any_sync(FULL, v0 || v1)) live |= 1u << r;
+            }
+            (void)me;
+            any = live != 0u;
 
-                    const float dL_dG = rb.y * dL_dalpha;
-                    const float gdx = Gv * dx[h], gdy = Gv * dy;
-                    v[0] = fmaf(-dL_dG, fmaf(gdx, ra.z, gdy * ra.w), v[0]);
-                    v[1] = fmaf(-dL_dG, fmaf(gdy, rb.x, gdx * ra.w), v[1]);
-                    const float hg = -0.5f * dL_dG;
-                    const float hgx = hg * gdx;
-                    v[2] = fmaf(hgx, dx[h], v[2]);
-                    v[3] = fmaf(hgx, dy, v[3]);
-                    v[4] = fmaf(hg * gdy, dy, v[4]);
-                    v[5] = fmaf(Gv, dL_dalpha, v[5]);
+            // Stage B: the sequential part (T, accum recurrences).  One 16x4 strip per step = one pixel
+            // PAIR per lane, all arithmetic packed (FFMA2).  Branch-free inside a strip: a rejected
+            // pixel runs the same arithmetic with alpha = G = 0, which leaves T, accum and every
+            // accumulator unchanged.
+#pragma unroll
+            for (int r = 0; r < NSTRIP; r++) {
+                if (!((live >> r) & 1u)) continue;               // warp-uniform
+                const float dy = __fsub_rn(ra.y, py_lane + (float)(PATCH_H * r));
+                const float4 pa = sm.pix[r][0][lane], pb = sm.pix[r][1][lane];
+                const float4 pc = sm.pix[r][2][lane], pd = sm.pix[r][3][lane];
+                const f2 g2[5] = {mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(pb.x, pb.y), mk2(pb.z, pb.w), mk2(pc.x, pc.y)};
+                const f2 ginv2 = mk2(pc.z, pc.w), nbg2 = mk2(pd.x, pd.y);
+#if EOGS_BWD_STATE_SMEM
+                const float4 st = sm.state[r][lane];
+                const f2 Told2 = mk2(st.x, st.y), accum_old2 = mk2(st.z, st.w);
+#else
+                const f2 Told2 = T2[r], accum_old2 = accum2[r];
+#endif
+                const f2 om2 = fma2(a2[r], bc2(-1.f), bc2(1.f));                // 1 - alpha
+                const f2 inv2 = mk2(fast_rcp(lo2(om2)), fast_rcp(hi2(om2)));    // exactly 1 for a rejected pixel
+                const f2 Tn2 = mul2(Told2, inv2);
+                const f2 w2 = mul2(a2[r], Tn2);
+                f2 cg2 = mul2(bc2(rc.w), ginv2);
+#pragma unroll
+                for (int ch = 0; ch < C; ch++) {
+                    fma2_acc(v2[6 + ch], w2, g2[ch]);
+                    fma2_acc(cg2, bc2(col[ch]), g2[ch]);
                 }
+                // accum = (colour blended behind this entry) . dL_dpixel
+                const f2 behind2 = fma2(accum_old2, bc2(-1.f), cg2);
+                const f2 dLa2 = fma2(nbg2, inv2, mul2(behind2, Tn2));           // dL/dalpha (finite; x0 below if rejected)
+                const f2 acc_new2 = fma2(a2[r], behind2, accum_old2);
+#if EOGS_BWD_STATE_SMEM
+                sm.state[r][lane] = make_float4(lo2(Tn2), hi2(Tn2), lo2(acc_new2), hi2(acc_new2));
+#else
+                T2[r] = Tn2; accum2[r] = acc_new2;
+#endif
+                const f2 dG2 = mul2(bc2(rb.y), dLa2);                            // dL/dG
+                const f2 gdx2 = mul2(Gv2[r], dx2), gdy2 = mul2(Gv2[r], bc2(dy));
+                fma2_acc(v2[0], dG2, fma2(gdx2, bc2(ra.z), mul2(gdy2, bc2(ra.w))));
+                fma2_acc(v2[1], dG2, fma2(gdy2, bc2(rb.x), mul2(gdx2, bc2(ra.w))));
+                const f2 hgx2 = mul2(dG2, gdx2);
+                fma2_acc(v2[2], hgx2, dx2);
+                fma2_acc(v2[3], hgx2, bc2(dy));
+                fma2_acc(v2[4], mul2(dG2, gdy2), bc2(dy));
+                fma2_acc(v2[5], Gv2[r], dLa2);
             }
             if (any) {
+                float v[NV];
+#pragma unroll
+                for (int k = 0; k < NV; k++) v[k] = lo2(v2[k]) + hi2(v2[k]);
                 warp_transpose_reduce<NV>(v, lane);
-                const uint32_t gid = __shfl_sync(FULL, cur_rid, e);
+                const uint32_t gid = sm.rid[stage][e];
                 if (my_slot >= 0) atomicAdd(grad_rec + (size_t)gid * GRAD_STRIDE + my_slot, v[0] * slot_scale);
             }
         }
@@ -239,8 +301,12 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
 {
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = band.rows();
     const dim3 grid((tiles_x + 1) / 2, (tiles_y + 1) / 2, 1);
+    constexpr size_t smem = sizeof(BwdWarpSmem) * BWD_WARPS;
+    cudaError_t attr_err = cudaSuccess;
     auto run = [&](auto kernel) {
-        kernel<<<grid, BWD_THREADS, 0, s>>>(
+        attr_err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (attr_err != cudaSuccess) return;
+        kernel<<<grid, BWD_THREADS, smem, s>>>(
             reinterpret_cast<const uint2*>(image + IL.ranges), point_list,
             reinterpret_cast<const float4*>(geom + GL.splat), bg, W, H, tiles_x, tiles_y,
             band.row_begin, band.height(H), reinterpret_cast<const float*>(image + IL.final_T),
@@ -249,6 +315,7 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
     if (channels == 5) run(blend_bwd_kernel<5>);
     else if (channels == 3) run(blend_bwd_kernel<3>);
     else { set_error("channels must be 3 or 5, got %d", channels); return -1; }
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(blend_bwd_kernel)");
     EOGS_LAUNCH_CHECK("blend_bwd_kernel");
     return 0;
 }

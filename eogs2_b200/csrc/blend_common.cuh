@@ -165,6 +165,12 @@ __device__ __forceinline__ float fast_rcp(float x) {      // x in [0.01, 1]: no 
     return r;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // exp(x) for x <= 0 through ex2.approx (relative error ~2^-22); backward only.
 __device__ __forceinline__ float fast_exp(float x) {
     float r;
