@@ -22,7 +22,7 @@ Gaussian parameters and to the affine camera matrix.
 --impl reference times the reference rasterizer's own CUDA kernels (oracle/_ref/libeogs_ref.so,
 compiled for sm_100a from /root/reference by oracle/ref_build/Makefile) on the same workload;
 when that library is absent it falls back to the CPU port.  N > 1: data parallel over views —
-each rank renders its own camera and the 14*P-float gradient bucket is all-reduced with NCCL
+each rank renders its own camera and the 16*P-float gradient bucket (written in place by the backward kernels) is all-reduced with NCCL
 inside the step (weak scaling).
 """
 from __future__ import annotations
@@ -157,7 +157,6 @@ def ours_e2e_factory(wl, dev):
 
     def step():
         bufs = pipe.get()                   # this step's inputs (copied from pinned host memory on the side stream)
-        pipe.submit(hsub)                   # next step's H2D overlaps this step's kernels
         t = {k: bufs[k].detach().requires_grad_(True) for k in names}
         view = wl["view"].clone().requires_grad_(True)
         settings = GaussianRasterizationSettings(
@@ -168,6 +167,7 @@ def ours_e2e_factory(wl, dev):
         color, radii, invd = GaussianRasterizer(settings)(
             means3D=t["means3D"], means2D=means2D, opacities=t["opacities"], colors_precomp=t["colors"],
             scales=t["scales"], rotations=t["rotations"])
+        pipe.submit(hsub)                   # next step's H2D (one copy per step) overlaps this step's blend kernels
         loss = (color * wl["dcol"]).sum()
         loss.backward()
         res = torch.cat([loss.detach().reshape(1), view.grad.reshape(-1)])
@@ -207,8 +207,8 @@ def ref_e2e_factory(wl, dev):
 
     def step():
         t = pipe.get()
-        pipe.submit(hsub)
         st, g = inner(t)
+        pipe.submit(hsub)
         # the Python half of the reference's backward (DGR __init__.py:172-202) and a loss read-back
         terms = R.grad_viewmatrix_terms(g, t["means3D"], wl["view"], IMG, IMG)
         loss = (st.color * wl["dcol"]).sum()
@@ -360,25 +360,27 @@ def main():
     bucket = None
     if world > 1:
         import torch.distributed as dist
-        bucket = torch.empty(14 * P_GAUSS + 16, dtype=torch.float32, device=dev)
-        last = {}
+        # ONE flat fp32 bucket holds every gradient the rasterizer returns for the replicated parameters —
+        # means3D 3, colours 5 (rgb -> f_dc, altitude -> xyz through the altitude colour, 1), opacity 1,
+        # scales 3, rotations 4 = 16 floats per Gaussian — plus the 16 camera sums.  The backward kernels
+        # write straight into views of it (no packing copies); it is all-reduced over NVLink inside the step.
+        P = P_GAUSS
+        bucket = torch.empty(16 * P + 16, dtype=torch.float32, device=dev)
+        views = {"means3D": bucket[0:3 * P].view(P, 3), "colors": bucket[3 * P:8 * P].view(P, 5),
+                 "opacity": bucket[8 * P:9 * P].view(P, 1), "scales": bucket[9 * P:12 * P].view(P, 3),
+                 "rotations": bucket[12 * P:16 * P].view(P, 4), "cam_sums": bucket[16 * P:]}
+        d = wl["dev"]
+        empty = torch.empty(0, device=dev)
 
         def step_dp():
-            st, g = step()
-            last["g"] = g
+            st = E.rasterize_forward_raw(wl["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"],
+                                         d["rotations"], 1.0, empty, wl["view"], IMG, IMG, False, False)
+            g = E.rasterize_backward_raw(st, wl["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"],
+                                         d["rotations"], 1.0, empty, wl["view"], wl["view"], wl["dcol"], wl["dinv"],
+                                         out=views)
             return st, g
 
         def post():
-            # flat fp32 bucket of the Adam groups' gradients (xyz 3, f_dc 3, opacity 1, scaling 3, rotation 4)
-            # + the camera sums, all-reduced over NVLink before the replicated optimiser step
-            g = last["g"]
-            P = P_GAUSS
-            bucket[0:3 * P].view(P, 3).copy_(g[3])                       # dL_dmeans3D
-            bucket[3 * P:6 * P].view(P, 3).copy_(g[1][:, :3])            # dL_dcolors rgb -> f_dc
-            bucket[6 * P:7 * P].view(P, 1).copy_(g[2])                   # dL_dopacity
-            bucket[7 * P:10 * P].view(P, 3).copy_(g[5])                  # dL_dscales
-            bucket[10 * P:14 * P].view(P, 4).copy_(g[6])                 # dL_drotations
-            bucket[14 * P:].copy_(g[7])
             dist.all_reduce(bucket)
         run_step = step_dp
     else:

@@ -82,6 +82,7 @@ def _info_host(device: torch.device) -> torch.Tensor:
     t = _pinned_info.get(key)
     if t is None:
         t = torch.zeros(2, dtype=torch.int32).pin_memory()
+        t = (t, t.numpy())                 # the numpy view reads the pinned words without a torch dispatch
         _pinned_info[key] = t
     return t
 
@@ -165,7 +166,7 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         geom_bytes = lib.eogs_geom_bytes(P)
         geom = torch.empty(geom_bytes + 256, dtype=torch.uint8, device=dev)
         info_dev = geom.data_ptr() + geom_bytes
-        info_host = _info_host(dev)
+        info_host, info_np = _info_host(dev)
 
         _cabi.check(lib.eogs_forward_geometry_band(
             stream, P, W, H, channels, rb, re, _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp),
@@ -174,8 +175,8 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         # The instance count sizes the binning buffers (reference: blocking cudaMemcpy,
         # rasterizer_impl.cu:284).
         torch.cuda.current_stream(dev).synchronize()
-        num_rendered = int(info_host[0].item()) & 0xFFFFFFFF
-        err = int(info_host[1].item())
+        num_rendered = int(info_np[0]) & 0xFFFFFFFF
+        err = int(info_np[1])
         if err & ERR_ALTITUDE_ABOVE_200:
             # reference: device printf("Point is too high") + __trap() (forward.cu:267-272)
             raise RuntimeError("Point is too high: a Gaussian's altitude exceeds 200 (depth = 200 - altitude < 0)")
@@ -197,25 +198,40 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
 
 def rasterize_backward_raw(state: ForwardState, bg, means3D, colors, opacities, scales, rotations,
                            scale_modifier, cov3D_precomp, viewmatrix, projmatrix, dL_dcolor,
-                           dL_dinvdepth, antialiasing=False, debug=False):
+                           dL_dinvdepth, antialiasing=False, debug=False, out=None):
     """Counterpart of _C.rasterize_gaussians_backward (DGR/rasterize_points.cu:126-224) plus the
     reductions of __init__.py:174-202.  Returns (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D,
-    dL_dcov3D | None, dL_dscales | None, dL_drotations | None, cam_sums[16])."""
+    dL_dcov3D | None, dL_dscales | None, dL_drotations | None, cam_sums[16]).
+
+    out: optional dict of preallocated contiguous fp32 CUDA tensors keyed "means2D", "colors",
+    "opacity", "means3D", "cov3D", "scales", "rotations", "cam_sums" — the kernels then write the
+    gradients straight into them (e.g. views of the data-parallel all-reduce bucket, dp.py)."""
     lib = _cabi.load()
     dev = means3D.device
     P, W, H, ch = state.P, state.W, state.H, state.channels
     rb, re = state.rows
     with torch.cuda.device(dev):
         opts = dict(dtype=torch.float32, device=dev)
-        dL_dmeans2D = torch.empty((P, 3), **opts)
-        dL_dcolors = torch.empty((P, ch), **opts)
-        dL_dopacity = torch.empty((P, 1), **opts)
-        dL_dmeans3D = torch.empty((P, 3), **opts)
-        cam_sums = torch.empty(16, **opts)
+        out = out or {}
+
+        def buf(key, shape):
+            t = out.get(key)
+            if t is None:
+                return torch.empty(shape, **opts)
+            if (t.device != dev or t.dtype != torch.float32 or not t.is_contiguous()
+                    or t.numel() != int(torch.Size(shape).numel())):
+                raise _cabi.EogsRasterError(f"out[{key!r}] must be a contiguous float32 tensor of shape {tuple(shape)} on {dev}")
+            return t.view(shape)
+
+        dL_dmeans2D = buf("means2D", (P, 3))
+        dL_dcolors = buf("colors", (P, ch))
+        dL_dopacity = buf("opacity", (P, 1))
+        dL_dmeans3D = buf("means3D", (P, 3))
+        cam_sums = buf("cam_sums", (16,))
         has_cov = cov3D_precomp is not None and cov3D_precomp.numel() != 0
-        dL_dcov3D = torch.empty((P, 6), **opts) if has_cov else None
-        dL_dscales = None if has_cov else torch.empty((P, 3), **opts)
-        dL_drotations = None if has_cov else torch.empty((P, 4), **opts)
+        dL_dcov3D = buf("cov3D", (P, 6)) if has_cov else None
+        dL_dscales = None if has_cov else buf("scales", (P, 3))
+        dL_drotations = None if has_cov else buf("rotations", (P, 4))
         if P == 0:
             cam_sums.zero_()
             return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales, dL_drotations, cam_sums
@@ -250,19 +266,36 @@ def rasterize_backward_raw(state: ForwardState, bg, means3D, colors, opacities, 
     return dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales, dL_drotations, cam_sums
 
 
+_assembly_cache: dict = {}
+
+
+def _assembly_matrix(device: torch.device, W: int, H: int) -> torch.Tensor:
+    """16x16 matrix M with grad_viewmatrix.flatten() = M @ cam_sums (built once per (device, W, H))."""
+    key = (str(device), int(W), int(H))
+    M = _assembly_cache.get(key)
+    if M is None:
+        M = torch.zeros(16, 16, dtype=torch.float32)
+        scale = (W / 2.0, H / 2.0, 1.0)
+        for r in range(3):
+            for c in range(2):
+                M[4 * r + c, 3 * c + r] += scale[r]          # diag(W/2, H/2, 1) @ (sum_b dL_dT[b]).view(2, 3)^T
+                M[4 * r + c, 6 + 2 * r + c] += 1.0           # means3D^T @ grad_means2D
+        for c in range(2):
+            M[12 + c, 12 + c] += 1.0                         # grad_means2D.sum(0)
+        M = M.to(device)
+        _assembly_cache[key] = M
+    return M
+
+
 def assemble_grad_viewmatrix(cam_sums: torch.Tensor, like: torch.Tensor, W: int, H: int) -> torch.Tensor:
     """grad_viewmatrix from the 14 kernel-side sums, term by term as __init__.py:172-202:
          [:3, :2] += diag(W/2, H/2, 1) @ (sum_b dL_dT[b]).view(2, 3)^T
          [:3, :3] += means3D^T @ grad_means2D          (third column is zero: grad_means2D.z == 0)
          [-1, :3] += grad_means2D.sum(0)
-    """
-    g = torch.zeros_like(like, dtype=torch.float32)
-    scale = torch.tensor([W / 2.0, H / 2.0, 1.0], dtype=torch.float32, device=cam_sums.device)
-    dL_dA = scale[:, None] * cam_sums[0:6].view(2, 3).t()
-    g[:3, :2] += dL_dA
-    g[:3, :2] += cam_sums[6:12].view(3, 2)
-    g[-1, :2] += cam_sums[12:14]
-    return g.to(like.dtype)
+    One matrix-vector product with a cached constant matrix: no host<->device traffic, so the
+    backward never synchronises (the reference issues ~10 small torch kernels here)."""
+    M = _assembly_matrix(cam_sums.device, W, H)
+    return torch.mv(M, cam_sums.to(torch.float32)).view(4, 4).to(like.dtype)
 
 
 def export_state(state: ForwardState) -> dict:

@@ -195,3 +195,30 @@ def test_single_call_c_entry_point_with_alloc_callbacks(cuda_dev):
     _cabi.check(rc, "eogs_rasterize_forward")
     torch.cuda.synchronize()
     assert n.value == st.num_rendered and torch.equal(color, st.color) and torch.equal(radii, st.radii)
+
+
+def test_backward_writes_into_caller_buffers(cuda_dev):
+    """out=: the backward kernels write the gradients straight into views of one flat bucket
+    (the data-parallel all-reduce buffer of bench.py / dp.py) — same values as fresh tensors."""
+    dev = cuda_dev
+    P, W, H = 5000, 128, 96
+    sc = S.make_scene(P, "trained", 71).to(dev)
+    view = S.make_camera(71).to(dev)
+    colors = S.colors_precomp(sc, view)
+    bg = S.background(71).to(dev)
+    dcol, dinv = (t.to(dev) for t in S.upstream_grads(5, H, W, 71, True))
+    empty = torch.empty(0, device=dev)
+    st = E.rasterize_forward_raw(bg, sc.means3D, colors, sc.opacities, sc.scales, sc.rotations, 1.0, empty, view, H, W)
+    args = (st, bg, sc.means3D, colors, sc.opacities, sc.scales, sc.rotations, 1.0, empty, view, view, dcol, dinv)
+    ref = E.rasterize_backward_raw(*args)
+    bucket = torch.full((16 * P + 16,), float("nan"), device=dev)
+    views = {"means3D": bucket[0:3 * P], "colors": bucket[3 * P:8 * P], "opacity": bucket[8 * P:9 * P],
+             "scales": bucket[9 * P:12 * P], "rotations": bucket[12 * P:16 * P], "cam_sums": bucket[16 * P:]}
+    got = E.rasterize_backward_raw(*args, out=views)
+    assert got[3].data_ptr() == bucket.data_ptr() and got[7].data_ptr() == bucket[16 * P:].data_ptr()
+    assert not torch.isnan(bucket).any()
+    for a, b in zip(got, ref):
+        if a is not None:
+            assert rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-4          # float atomics: order differs run to run
+    with pytest.raises(_cabi.EogsRasterError):
+        E.rasterize_backward_raw(*args, out={"means3D": torch.empty(7, device=dev)})
