@@ -164,9 +164,14 @@ class HostInputPipeline:
         self.next_slot ^= 1
         if self.slots[s] is None or any(self.slots[s][k].shape != v.shape or self.slots[s][k].dtype != v.dtype
                                         for k, v in host_tensors.items()):
-            with torch.cuda.device(self.device):
+            # Allocate ON the copy stream: a block taken from the consumer stream's pool may have been
+            # freed there a moment ago (e.g. the rasterizer's binning scratch) with kernels that still
+            # use it queued on the consumer stream — the copy stream would overwrite it under them.
+            with torch.cuda.device(self.device), torch.cuda.stream(self.copy_stream):
                 self.slots[s] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
                                  for k, v in host_tensors.items()}
+            for t in self.slots[s].values():
+                t.record_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.copy_stream):
             if self.free[s] is not None:
                 self.copy_stream.wait_event(self.free[s])
