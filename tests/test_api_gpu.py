@@ -222,3 +222,38 @@ def test_backward_writes_into_caller_buffers(cuda_dev):
             assert rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-4          # float atomics: order differs run to run
     with pytest.raises(_cabi.EogsRasterError):
         E.rasterize_backward_raw(*args, out={"means3D": torch.empty(7, device=dev)})
+
+
+def test_three_channel_specialisation_matches_five_channel_render(cuda_dev):
+    """C = 3 (grey/PAN, altitude, opacity — SURVEY.md §8 a19) behind the same API: channels are
+    blended independently, so the C = 3 render must equal the first three channels of the C = 5
+    render bit for bit, and with no upstream gradient on channels 3, 4 the geometry gradients agree."""
+    dev = cuda_dev
+    P, W, H = 8000, 200, 136
+    sc = S.make_scene(P, "trained", 81).to(dev)
+    view = S.make_camera(81).to(dev)
+    c5 = S.colors_precomp(sc, view)
+    c3 = torch.stack([c5[:, :3].mean(1), c5[:, 3], c5[:, 4]], 1).contiguous()         # grey, altitude, 1
+    c5b = torch.cat([c3, c5[:, :2]], 1).contiguous()
+    bg5 = S.background(81).to(dev)
+    bg3 = bg5[[0, 3, 4]].contiguous()
+    bg5b = torch.cat([bg3, bg5[:2]]).contiguous()
+    dcol, dinv = (t.to(dev) for t in S.upstream_grads(5, H, W, 81, True))
+    dcol5 = dcol.clone(); dcol5[3:] = 0
+    dcol3 = dcol[:3].contiguous()
+    empty = torch.empty(0, device=dev)
+
+    def run(colors, bg, dc):
+        st = E.rasterize_forward_raw(bg, sc.means3D, colors, sc.opacities, sc.scales, sc.rotations, 1.0, empty, view, H, W)
+        g = E.rasterize_backward_raw(st, bg, sc.means3D, colors, sc.opacities, sc.scales, sc.rotations, 1.0, empty,
+                                     view, view, dc, dinv)
+        return st, g
+    st3, g3 = run(c3, bg3, dcol3)
+    st5, g5 = run(c5b, bg5b, dcol5)
+    assert st3.color.shape == (3, H, W)
+    assert torch.equal(st3.color, st5.color[:3]) and torch.equal(st3.invdepth, st5.invdepth)
+    assert torch.equal(st3.radii, st5.radii) and st3.num_rendered == st5.num_rendered
+    assert torch.equal(E.export_state(st3)["n_contrib"], E.export_state(st5)["n_contrib"])
+    assert rel(g3[1].cpu().numpy(), g5[1][:, :3].cpu().numpy()) < 1e-4                 # dL_dcolors
+    for k in (0, 2, 3, 5, 6, 7):                                                       # means2D, opacity, means3D, scales, rotations, cam sums
+        assert rel(g3[k].cpu().numpy(), g5[k].cpu().numpy()) < 1e-4, k
