@@ -105,7 +105,8 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
     // values; the radix sort is stable and ids come in ascending, which yields the tie order.
     size_t need = 0;
     cub::DoubleBuffer<uint32_t> keys(key_in, key_out);
-    cub::DoubleBuffer<uint32_t> vals(id_in, order);
+    // preprocess wrote 0..P-1 into `order` (see launch_preprocess_fwd): 4 passes land back in `order`
+    cub::DoubleBuffer<uint32_t> vals(order, id_in);
     EOGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, P, 0, 32, s));
     if (need > L.temp_bytes) { set_error("depth sort temp %zu > %zu", need, L.temp_bytes); return -3; }
     need = L.temp_bytes;
@@ -135,10 +136,11 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
 // (rasterizer_impl.cu:96-108).
 constexpr int EMIT_THREADS = 256;
 
+template <typename KeyT>
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_instances_kernel(int P, int grid_x, uint32_t band_y0, const uint32_t* __restrict__ order,
                       const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect,
-                      uint32_t* __restrict__ tile_keys, uint32_t* __restrict__ ids)
+                      KeyT* __restrict__ tile_keys, uint32_t* __restrict__ ids)
 {
     __shared__ uint32_t s_end[EMIT_THREADS];
     __shared__ uint32_t s_id[EMIT_THREADS];
@@ -175,25 +177,40 @@ emit_instances_kernel(int P, int grid_x, uint32_t band_y0, const uint32_t* __res
         const uint32_t x0 = r.x & 0xFFFFu, y0 = r.x >> 16, x1 = r.y & 0xFFFFu;
         const uint32_t w = x1 - x0;
         const uint32_t ry = local / w, rx = local - ry * w;   // row-major over (y, x), rasterizer_impl.cu:96-99
-        tile_keys[block_start + t] = (y0 - band_y0 + ry) * (uint32_t)grid_x + (x0 + rx);   // band-relative tile id
+        tile_keys[block_start + t] = (KeyT)((y0 - band_y0 + ry) * (uint32_t)grid_x + (x0 + rx));   // band-relative tile id
         ids[block_start + t] = s_id[lo];
     }
 }
 
 // ---- stage 2c: tile ranges -------------------------------------------------------------------
-// identifyTileRanges (rasterizer_impl.cu:116-138) on 32-bit tile keys.
+// identifyTileRanges (rasterizer_impl.cu:116-138) on the sorted tile keys.  Each thread scans
+// KPT consecutive keys fetched with one 16-byte load (the reference: one thread, two scalar loads
+// per key), so the kernel streams at HBM rate; boundaries are rare (one per non-empty tile).
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(uint32_t I, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges)
+tile_ranges_kernel(uint32_t I, const KeyT* __restrict__ keys, uint2* __restrict__ ranges)
 {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= I) return;
-    const uint32_t cur = __ldg(keys + idx);
-    if (idx == 0) ranges[cur].x = 0;
-    else {
-        const uint32_t prev = __ldg(keys + idx - 1);
-        if (cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
+    constexpr uint32_t KPT = 16 / sizeof(KeyT);               // keys per thread: 8 (u16) or 4 (u32)
+    const uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * KPT;
+    if (base >= I) return;
+    KeyT k[KPT];
+    if (base + KPT <= I) {
+        *reinterpret_cast<uint4*>(k) = __ldg(reinterpret_cast<const uint4*>(keys + base));    // base*sizeof(KeyT) % 16 == 0
+    } else {
+#pragma unroll
+        for (uint32_t j = 0; j < KPT; j++) k[j] = base + j < I ? __ldg(keys + base + j) : (KeyT)0;
     }
-    if (idx == I - 1) ranges[cur].y = I;
+    uint32_t prev = base > 0 ? (uint32_t)__ldg(keys + base - 1) : 0u;
+    if (base == 0) ranges[(uint32_t)k[0]].x = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < KPT; j++) {
+        const uint32_t idx = base + j;
+        if (idx >= I) break;
+        const uint32_t cur = (uint32_t)k[j];
+        if (idx > 0 && cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
+        if (idx == I - 1) ranges[cur].y = I;
+        prev = cur;
+    }
 }
 
 // getHigherMsb (rasterizer_impl.cu:35-50): number of key bits needed for tile ids
@@ -217,31 +234,44 @@ int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, c
     EOGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
     if (I == 0) return 0;
 
-    uint32_t* key_in = reinterpret_cast<uint32_t*>(binning + BL.key_in);
-    uint32_t* key_out = reinterpret_cast<uint32_t*>(binning + BL.key_out);
     uint32_t* val_in = reinterpret_cast<uint32_t*>(binning + BL.val_in);
-
-    emit_instances_kernel<<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(
-        P, grid_x, (uint32_t)band.row_begin, reinterpret_cast<const uint32_t*>(geom + GL.order),
-        reinterpret_cast<const uint32_t*>(geom + GL.offsets),
-        reinterpret_cast<const uint2*>(geom + GL.rect), key_in, val_in);
-    EOGS_LAUNCH_CHECK("emit_instances_kernel");
-    prof_mark(s, ST_EMIT);
-
     const int bit = (int)higher_msb(tiles);
-    cub::DoubleBuffer<uint32_t> keys(key_in, key_out);
-    cub::DoubleBuffer<uint32_t> vals(val_in, point_list);
-    size_t need = 0;
-    EOGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)I, 0, bit, s));
-    if (need > BL.temp_bytes) { set_error("tile sort temp %zu > %zu", need, BL.temp_bytes); return -3; }
-    need = BL.temp_bytes;
-    EOGS_CUDA(cub::DeviceRadixSort::SortPairs(binning + BL.temp, need, keys, vals, (int)I, 0, bit, s));
-    if (vals.Current() != point_list)
-        EOGS_CUDA(cudaMemcpyAsync(point_list, vals.Current(), (size_t)I * 4, cudaMemcpyDeviceToDevice, s));
 
-    prof_mark(s, ST_TILE_SORT);
-    tile_ranges_kernel<<<(I + 255) / 256, 256, 0, s>>>(I, keys.Current(), ranges);
-    EOGS_LAUNCH_CHECK("tile_ranges_kernel");
+    // Tile ids fit 16 bits up to 65 535 tiles (4096^2 images): 16-bit sort keys cut the traffic of
+    // every sort pass from 16 to 12 bytes per instance.  Larger grids sort 32-bit keys.
+    auto run = [&](auto key_tag) -> int {
+        using KeyT = decltype(key_tag);
+        KeyT* key_in = reinterpret_cast<KeyT*>(binning + BL.key_in);
+        KeyT* key_out = reinterpret_cast<KeyT*>(binning + BL.key_out);
+        // An onesweep sort of `bit` bits takes ceil(bit/8) passes and ping-pongs between the two value
+        // buffers: emit into the one that makes the LAST pass land in point_list (no copy afterwards).
+        const bool even_passes = (((bit + 7) / 8) & 1) == 0;
+        uint32_t* ids_first = even_passes ? point_list : val_in;
+        uint32_t* ids_other = even_passes ? val_in : point_list;
+        emit_instances_kernel<KeyT><<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(
+            P, grid_x, (uint32_t)band.row_begin, reinterpret_cast<const uint32_t*>(geom + GL.order),
+            reinterpret_cast<const uint32_t*>(geom + GL.offsets),
+            reinterpret_cast<const uint2*>(geom + GL.rect), key_in, ids_first);
+        EOGS_LAUNCH_CHECK("emit_instances_kernel");
+        prof_mark(s, ST_EMIT);
+
+        cub::DoubleBuffer<KeyT> keys(key_in, key_out);
+        cub::DoubleBuffer<uint32_t> vals(ids_first, ids_other);
+        size_t need = 0;
+        EOGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)I, 0, bit, s));
+        if (need > BL.temp_bytes) { set_error("tile sort temp %zu > %zu", need, BL.temp_bytes); return -3; }
+        need = BL.temp_bytes;
+        EOGS_CUDA(cub::DeviceRadixSort::SortPairs(binning + BL.temp, need, keys, vals, (int)I, 0, bit, s));
+        if (vals.Current() != point_list)
+            EOGS_CUDA(cudaMemcpyAsync(point_list, vals.Current(), (size_t)I * 4, cudaMemcpyDeviceToDevice, s));
+        prof_mark(s, ST_TILE_SORT);
+
+        constexpr uint32_t per_block = 256u * (16u / sizeof(KeyT));
+        tile_ranges_kernel<KeyT><<<(I + per_block - 1) / per_block, 256, 0, s>>>(I, keys.Current(), ranges);
+        EOGS_LAUNCH_CHECK("tile_ranges_kernel");
+        return 0;
+    };
+    if (int rc = tiles <= 0xFFFFu ? run(uint16_t{}) : run(uint32_t{})) return rc;
     prof_mark(s, ST_RANGES);
     return 0;
 }

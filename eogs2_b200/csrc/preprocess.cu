@@ -165,7 +165,7 @@ int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int ch
             cov3D_precomp, opacities, colors, view, scale_modifier, antialiasing, align_mask, radii,
             reinterpret_cast<float4*>(geom + L.splat), reinterpret_cast<float*>(geom + L.depth),
             reinterpret_cast<uint2*>(geom + L.rect), reinterpret_cast<uint32_t*>(geom + L.tiles),
-            reinterpret_cast<uint32_t*>(geom + L.key_in), reinterpret_cast<uint32_t*>(geom + L.id_in),
+            reinterpret_cast<uint32_t*>(geom + L.key_in), reinterpret_cast<uint32_t*>(geom + L.order),
             info_dev);
     };
     if (channels == 5) args(preprocess_fwd_kernel<5>);
