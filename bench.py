@@ -144,7 +144,7 @@ def ours_step_factory(wl, dev):
     return step
 
 
-def ours_e2e_factory(wl, dev):
+def ours_e2e_factory(wl, dev, world=1):
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     h = wl["host"]
     names = ["means3D", "scales", "rotations", "opacities", "colors"]
@@ -170,7 +170,15 @@ def ours_e2e_factory(wl, dev):
         pipe.submit(hsub)                   # next step's H2D (one copy per step) overlaps this step's blend kernels
         loss = (color * wl["dcol"]).sum()
         loss.backward()
-        res = torch.cat([loss.detach().reshape(1), view.grad.reshape(-1)])
+        if world > 1:
+            # data parallel over views: the step is not finished before the gradients are summed over ranks
+            import torch.distributed as dist
+            flat = torch.cat([t[k].grad.reshape(-1) for k in names] + [view.grad.reshape(-1)])
+            dist.all_reduce(flat)
+            view_grad = flat[-16:]
+        else:
+            view_grad = view.grad.reshape(-1)
+        res = torch.cat([loss.detach().reshape(1), view_grad])
         out_host.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(out_host[0])
@@ -407,7 +415,7 @@ def main():
     I = st.num_rendered
 
     # e2e through the public API with host inputs
-    e2e_step, h2d, d2h = ours_e2e_factory(wl, dev)
+    e2e_step, h2d, d2h = ours_e2e_factory(wl, dev, world)
     e2e_ms = None
     if not args.no_e2e:
         e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, world)

@@ -62,6 +62,18 @@ SIGNATURES = {
     "eogs_export_state_band": (C.c_int, [
         c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, c_ptr, c_ptr, c_ptr,
         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "eogs_forward_geometry_params_band": (C.c_int, [
+        c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,            # stream, P, W, H, row_begin, row_end
+        c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,                # xyz, log_scales, raw_rot, logits, f_dc, alt_affine
+        c_f32p, C.c_float, C.c_int,                                    # viewmatrix, scale_modifier, antialiasing
+        c_ptr, c_ptr, c_ptr, c_ptr]),                                  # radii, geom, info_dev, info_host
+    "eogs_backward_params_band": (C.c_int, [
+        c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32,
+        c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,                        # xyz, log_scales, raw_rot, logits, alt_affine
+        c_f32p, c_f32p, C.c_float, C.c_int, c_f32p,                    # view, proj, scale_modifier, antialiasing, bg
+        c_ptr, c_ptr, c_ptr, c_ptr, c_f32p, c_f32p,                    # radii, geom, point_list, image, dL_dpix, dL_dinvdepth
+        c_f32p,                                                        # grad_scratch
+        c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
     "eogs_mark_visible": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_f32p, c_ptr]),
     "eogs_profile_enable": (C.c_int, [C.c_int]),
     "eogs_profile_read": (C.c_int, [c_ptr, C.c_int]),
@@ -70,7 +82,7 @@ SIGNATURES = {
         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 

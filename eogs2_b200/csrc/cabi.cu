@@ -129,8 +129,8 @@ EOGS_API size_t eogs_image_bytes_band(int W, int H, int row_begin, int row_end) 
 }
 EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t I) { return binning_layout(W, H, I).total; }
 
-EOGS_API int eogs_forward_geometry_band(eogs_stream_t stream, int P, int W, int H, int channels,
-                          int row_begin, int row_end,
+static int forward_geometry_impl(eogs_stream_t stream, int P, int W, int H, int channels,
+                          int row_begin, int row_end, bool raw_params, const float* alt_affine,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities, const float* colors,
                           const float* viewmatrix, float scale_modifier, int antialiasing,
@@ -149,15 +149,42 @@ EOGS_API int eogs_forward_geometry_band(eogs_stream_t stream, int P, int W, int 
     if (P > 0) {
         const GeomLayout L = geom_layout(P);
         char* g = static_cast<char*>(geom);
-        if (int rc = launch_preprocess_fwd(s, P, W, H, band, channels, means3D, scales, rotations, cov3D_precomp,
-                                           opacities, colors, viewmatrix, scale_modifier, antialiasing != 0,
-                                           radii, g, L, info_dev)) return rc;
+        if (int rc = launch_preprocess_fwd(s, P, W, H, band, channels, raw_params, means3D, scales, rotations,
+                                           cov3D_precomp, opacities, colors, viewmatrix, alt_affine, scale_modifier,
+                                           antialiasing != 0, radii, g, L, info_dev)) return rc;
         prof_mark(s, ST_PREPROCESS);
         if (int rc = launch_depth_order(s, P, g, L, info_dev)) return rc;
     }
     if (info_host)
         EOGS_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(eogs_forward_info), cudaMemcpyDeviceToHost, s));
     return 0;
+}
+
+EOGS_API int eogs_forward_geometry_band(eogs_stream_t stream, int P, int W, int H, int channels,
+                          int row_begin, int row_end,
+                          const float* means3D, const float* scales, const float* rotations,
+                          const float* cov3D_precomp, const float* opacities, const float* colors,
+                          const float* viewmatrix, float scale_modifier, int antialiasing,
+                          int32_t* radii, void* geom, eogs_forward_info* info_dev,
+                          eogs_forward_info* info_host)
+{
+    return forward_geometry_impl(stream, P, W, H, channels, row_begin, row_end, false, nullptr, means3D, scales,
+                                 rotations, cov3D_precomp, opacities, colors, viewmatrix, scale_modifier, antialiasing,
+                                 radii, geom, info_dev, info_host);
+}
+
+EOGS_API int eogs_forward_geometry_params_band(eogs_stream_t stream, int P, int W, int H,
+                          int row_begin, int row_end,
+                          const float* xyz, const float* log_scales, const float* raw_rotations,
+                          const float* opacity_logits, const float* features_dc, const float* alt_affine,
+                          const float* viewmatrix, float scale_modifier, int antialiasing,
+                          int32_t* radii, void* geom, eogs_forward_info* info_dev,
+                          eogs_forward_info* info_host)
+{
+    if (!alt_affine || !log_scales || !raw_rotations || !features_dc) { set_error("null argument"); return -4; }
+    return forward_geometry_impl(stream, P, W, H, 5, row_begin, row_end, true, alt_affine, xyz, log_scales,
+                                 raw_rotations, nullptr, opacity_logits, features_dc, viewmatrix, scale_modifier,
+                                 antialiasing, radii, geom, info_dev, info_host);
 }
 
 EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, int channels,
@@ -245,8 +272,9 @@ EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, i
                                binning, *image, bg, out_color, out_invdepth);
 }
 
-EOGS_API int eogs_backward_band(eogs_stream_t stream, int P, int W, int H, int channels,
-                  int row_begin, int row_end, uint32_t num_instances,
+static int backward_impl(eogs_stream_t stream, int P, int W, int H, int channels,
+                  int row_begin, int row_end, bool raw_params, const float* alt_affine, float* alt_sums,
+                  uint32_t num_instances,
                   const float* means3D, const float* scales, const float* rotations,
                   const float* cov3D_precomp, const float* opacities, const float* colors,
                   const float* viewmatrix, const float* projmatrix,
@@ -264,7 +292,11 @@ EOGS_API int eogs_backward_band(eogs_stream_t stream, int P, int W, int H, int c
     if (int rc = check_band(H, band)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (!cam_sums) { set_error("null argument"); return -4; }
-    if (P == 0) { EOGS_CUDA(cudaMemsetAsync(cam_sums, 0, 16 * sizeof(float), s)); return 0; }
+    if (P == 0) {
+        EOGS_CUDA(cudaMemsetAsync(cam_sums, 0, 16 * sizeof(float), s));
+        if (alt_sums) EOGS_CUDA(cudaMemsetAsync(alt_sums, 0, 4 * sizeof(float), s));
+        return 0;
+    }
     if (!means3D || !opacities || !viewmatrix || !projmatrix || !bg || !radii || !geom || !image || !dL_dpix ||
         !grad_scratch || !dL_dmeans2D || !dL_dcolors || !dL_dopacity || !dL_dmeans3D) {
         set_error("null argument"); return -4;
@@ -281,12 +313,55 @@ EOGS_API int eogs_backward_band(eogs_stream_t stream, int P, int W, int H, int c
                                       grad_scratch)) return rc;
     }
     prof_mark(s, ST_BLEND_BWD);
-    const int rc_pre = launch_preprocess_bwd(s, P, W, H, channels, means3D, scales, rotations, cov3D_precomp, opacities,
+    const int rc_pre = launch_preprocess_bwd(s, P, W, H, channels, raw_params, alt_affine, alt_sums, means3D, scales, rotations, cov3D_precomp, opacities,
                                  viewmatrix, projmatrix, scale_modifier, antialiasing != 0, radii, grad_scratch,
                                  dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales,
                                  dL_drotations, cam_sums);
     prof_mark(s, ST_PREPROCESS_BWD);
     return rc_pre;
+}
+
+EOGS_API int eogs_backward_band(eogs_stream_t stream, int P, int W, int H, int channels,
+                  int row_begin, int row_end, uint32_t num_instances,
+                  const float* means3D, const float* scales, const float* rotations,
+                  const float* cov3D_precomp, const float* opacities, const float* colors,
+                  const float* viewmatrix, const float* projmatrix,
+                  float scale_modifier, int antialiasing, const float* bg,
+                  const int32_t* radii, const void* geom, const uint32_t* point_list,
+                  const void* image, const float* dL_dpix, const float* dL_dinvdepth,
+                  float* grad_scratch,
+                  float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
+                  float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
+                  float* dL_drotations, float* cam_sums)
+{
+    return backward_impl(stream, P, W, H, channels, row_begin, row_end, false, nullptr, nullptr, num_instances, means3D,
+                         scales, rotations, cov3D_precomp, opacities, colors, viewmatrix, projmatrix, scale_modifier,
+                         antialiasing, bg, radii, geom, point_list, image, dL_dpix, dL_dinvdepth, grad_scratch,
+                         dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dscales, dL_drotations,
+                         cam_sums);
+}
+
+EOGS_API int eogs_backward_params_band(eogs_stream_t stream, int P, int W, int H,
+                  int row_begin, int row_end, uint32_t num_instances,
+                  const float* xyz, const float* log_scales, const float* raw_rotations,
+                  const float* opacity_logits, const float* alt_affine,
+                  const float* viewmatrix, const float* projmatrix,
+                  float scale_modifier, int antialiasing, const float* bg,
+                  const int32_t* radii, const void* geom, const uint32_t* point_list,
+                  const void* image, const float* dL_dpix, const float* dL_dinvdepth,
+                  float* grad_scratch,
+                  float* dL_dmeans2D, float* dL_dfeatures_dc, float* dL_dopacity_logits,
+                  float* dL_dxyz, float* dL_dlog_scales, float* dL_draw_rotations,
+                  float* cam_sums, float* alt_sums)
+{
+    if (!alt_affine || !alt_sums || !log_scales || !raw_rotations || !dL_dlog_scales || !dL_draw_rotations) {
+        set_error("null argument"); return -4;
+    }
+    return backward_impl(stream, P, W, H, 5, row_begin, row_end, true, alt_affine, alt_sums, num_instances, xyz,
+                         log_scales, raw_rotations, nullptr, opacity_logits, nullptr, viewmatrix, projmatrix,
+                         scale_modifier, antialiasing, bg, radii, geom, point_list, image, dL_dpix, dL_dinvdepth,
+                         grad_scratch, dL_dmeans2D, dL_dfeatures_dc, dL_dopacity_logits, dL_dxyz, nullptr,
+                         dL_dlog_scales, dL_draw_rotations, cam_sums);
 }
 
 EOGS_API int eogs_backward(eogs_stream_t stream, int P, int W, int H, int channels,

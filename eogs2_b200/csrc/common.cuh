@@ -100,10 +100,10 @@ void prof_begin(cudaStream_t s);
 void prof_mark(cudaStream_t s, int stage);
 
 // ---- stage launchers (one per .cu) --------------------------------------------------------
-int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int channels,
+int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int channels, bool raw_params,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities, const float* colors,
-                          const float* view, float scale_modifier, bool antialiasing,
+                          const float* view, const float* alt_affine, float scale_modifier, bool antialiasing,
                           int32_t* radii, char* geom, const GeomLayout& L, eogs_forward_info* info_dev);
 
 int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
@@ -122,7 +122,8 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
                      const ImageLayout& IL, const float* bg, const float* dL_dpix,
                      const float* dL_dinvdepth, float* grad_rec);
 
-int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels,
+int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels, bool raw_params,
+                          const float* alt_affine, float* alt_sums,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities,
                           const float* view, const float* proj, float scale_modifier,

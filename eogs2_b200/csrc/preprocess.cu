@@ -27,13 +27,19 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, float*
     for (int i = (nvec << 2) + threadIdx.x; i < nfloat; i += PRE_THREADS) dst[i] = __ldg(s + i);
 }
 
-template <int C>
+// RAW = the fused render path (eogs_forward_geometry_params): `scales` holds log-scales, `rotations`
+// un-normalised quaternions, `opacities` logits and `colors` the SH DC coefficients [P,3]; the
+// activations and colors_precomp = [SH2RGB(f_dc), altitude, 1] (renderer.py:84-107) are computed here
+// instead of by ~10 torch kernels and 5 P-sized temporaries.  alt_affine[4]: altitude = a . xyz + b
+// (AffineCamera.ECEF_to_UVA, scene/cameras/affine_cameras.py:432-438, third component).
+template <int C, bool RAW>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, int band_y1,
                       const float* __restrict__ means3D, const float* __restrict__ scales,
                       const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
                       const float* __restrict__ opacities, const float* __restrict__ colors,
-                      const float* __restrict__ view, float scale_modifier, bool antialiasing,
+                      const float* __restrict__ view, const float* __restrict__ alt_affine,
+                      float scale_modifier, bool antialiasing,
                       int align_mask, int32_t* __restrict__ radii, float4* __restrict__ splat,
                       float* __restrict__ depth, uint2* __restrict__ rect,
                       uint32_t* __restrict__ tiles, uint32_t* __restrict__ key_in,
@@ -41,13 +47,14 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
 {
     __shared__ __align__(16) float s_mean[PRE_THREADS * 3];
     __shared__ __align__(16) float s_scale[PRE_THREADS * 3];
-    __shared__ __align__(16) float s_color[PRE_THREADS * C];
+    constexpr int CIN = RAW ? 3 : C;                 // floats per Gaussian in `colors`
+    __shared__ __align__(16) float s_color[PRE_THREADS * CIN];
     __shared__ float s_view[16];
 
     const int base = blockIdx.x * PRE_THREADS;
     stage_rows<3>(means3D, s_mean, base, P, align_mask & 1);
     if (scales) stage_rows<3>(scales, s_scale, base, P, align_mask & 2);
-    stage_rows<C>(colors, s_color, base, P, align_mask & 4);
+    stage_rows<CIN>(colors, s_color, base, P, align_mask & 4);
     if (threadIdx.x < 16) s_view[threadIdx.x] = __ldg(view + threadIdx.x);
     __syncthreads();
 
@@ -72,9 +79,13 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
 #pragma unroll
         for (int k = 0; k < 6; k++) c3[k] = __ldg(cov3D_precomp + 6 * (size_t)idx + k);
     } else {
-        const float4 q = __ldg(rotations + idx);
-        cov3d_from_scale_rot(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1],
-                             s_scale[3 * threadIdx.x + 2], scale_modifier, q, c3);
+        float4 q = __ldg(rotations + idx);
+        float sx = s_scale[3 * threadIdx.x], sy = s_scale[3 * threadIdx.x + 1], sz = s_scale[3 * threadIdx.x + 2];
+        if (RAW) {
+            sx = expf(sx); sy = expf(sy); sz = expf(sz);
+            q = act_normalize(q, quat_norm_clamped(q));
+        }
+        cov3d_from_scale_rot(sx, sy, sz, scale_modifier, q, c3);
     }
 
     const Affine2x3 T = make_T(s_view, W, H);
@@ -126,11 +137,20 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
                 out_rect = make_uint2((uint32_t)x0 | ((uint32_t)y0b << 16), (uint32_t)x1 | ((uint32_t)y1b << 16));
                 out_depth = d;
                 out_key = __float_as_uint(d);
-                const float op = __fmul_rn(__ldg(opacities + idx), aa_scale);
-                const float* col = s_color + C * threadIdx.x;
+                float op_in = __ldg(opacities + idx);
+                if (RAW) op_in = act_sigmoid(op_in);
+                const float op = __fmul_rn(op_in, aa_scale);
+                const float* col = s_color + CIN * threadIdx.x;
                 float cc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                if (RAW) {
+                    cc[0] = act_sh2rgb(col[0]); cc[1] = act_sh2rgb(col[1]); cc[2] = act_sh2rgb(col[2]);
+                    cc[3] = __fadd_rn(__fmaf_rn(pz, __ldg(alt_affine + 2), __fmaf_rn(py, __ldg(alt_affine + 1),
+                                      __fmul_rn(px, __ldg(alt_affine)))), __ldg(alt_affine + 3));
+                    cc[4] = 1.f;
+                } else {
 #pragma unroll
-                for (int k = 0; k < C; k++) cc[k] = col[k];
+                    for (int k = 0; k < C; k++) cc[k] = col[k];
+                }
                 r0 = make_float4(mx, my, conic_x, conic_y);
                 r1 = make_float4(conic_z, op, cc[0], cc[1]);
                 r2 = make_float4(cc[2], cc[3], cc[4], __fdiv_rn(1.f, d));
@@ -148,10 +168,10 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
     rec[0] = r0; rec[1] = r1; rec[2] = r2;
 }
 
-int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int channels,
+int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int channels, bool raw_params,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities, const float* colors,
-                          const float* view, float scale_modifier, bool antialiasing,
+                          const float* view, const float* alt_affine, float scale_modifier, bool antialiasing,
                           int32_t* radii, char* geom, const GeomLayout& L, eogs_forward_info* info_dev)
 {
     const int grid_x = (W + TILE - 1) / TILE, grid_y = (H + TILE - 1) / TILE;
@@ -162,14 +182,18 @@ int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int ch
     auto args = [&](auto kernel) {
         kernel<<<blocks, PRE_THREADS, 0, s>>>(
             P, W, H, grid_x, grid_y, band.row_begin, band.row_end, means3D, scales, reinterpret_cast<const float4*>(rotations),
-            cov3D_precomp, opacities, colors, view, scale_modifier, antialiasing, align_mask, radii,
+            cov3D_precomp, opacities, colors, view, alt_affine, scale_modifier, antialiasing, align_mask, radii,
             reinterpret_cast<float4*>(geom + L.splat), reinterpret_cast<float*>(geom + L.depth),
             reinterpret_cast<uint2*>(geom + L.rect), reinterpret_cast<uint32_t*>(geom + L.tiles),
             reinterpret_cast<uint32_t*>(geom + L.key_in), reinterpret_cast<uint32_t*>(geom + L.order),
             info_dev);
     };
-    if (channels == 5) args(preprocess_fwd_kernel<5>);
-    else if (channels == 3) args(preprocess_fwd_kernel<3>);
+    if (raw_params) {
+        if (channels != 5 || cov3D_precomp || !alt_affine) { set_error("the fused-parameter path renders 5 channels from scales+rotations"); return -1; }
+        args(preprocess_fwd_kernel<5, true>);
+    }
+    else if (channels == 5) args(preprocess_fwd_kernel<5, false>);
+    else if (channels == 3) args(preprocess_fwd_kernel<3, false>);
     else { set_error("channels must be 3 or 5, got %d", channels); return -1; }
     EOGS_LAUNCH_CHECK("preprocess_fwd_kernel");
     return 0;

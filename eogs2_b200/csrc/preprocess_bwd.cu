@@ -22,9 +22,18 @@ namespace eogs {
 constexpr int PBW_THREADS = 256;
 constexpr int NSUMS = 14;
 
-template <int C>
+// RAW = backward of the fused render path: the inputs are the raw parameters (log-scales,
+// un-normalised quaternions, opacity logits) and the gradients are chained through the activations and
+// through colors_precomp = [SH2RGB(f_dc), altitude(xyz), 1] in this kernel:
+//   dL_dcolors    -> dL_df_dc [P,3]  = C0 * dL_drgb            (utils/sh_utils.py:125-126)
+//   dL_dmeans3D  += a * dL_daltitude                           (ECEF_to_UVA, affine_cameras.py:432-438)
+//   alt_sums[4]   = sum_p dL_daltitude * (x, y, z, 1)          (gradient of the altitude affine row)
+//   dL_dopacity   -> dL_dlogit      = dL_dop * op * (1 - op)
+//   dL_dscales    -> dL_dlog_scale  = dL_ds * s
+//   dL_drotations -> dL_draw_quat   = (dL_dq - q (q . dL_dq)) / max(|r|, 1e-12)
+template <int C, bool RAW>
 __global__ void __launch_bounds__(PBW_THREADS)
-preprocess_bwd_kernel(int P, int W, int H,
+preprocess_bwd_kernel(int P, int W, int H, const float* __restrict__ alt_affine, float* __restrict__ alt_sums,
                       const float* __restrict__ means3D, const float* __restrict__ scales,
                       const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
                       const float* __restrict__ opacities, const float* __restrict__ view,
@@ -36,7 +45,8 @@ preprocess_bwd_kernel(int P, int W, int H,
                       float4* __restrict__ dL_drotations, float* __restrict__ cam_sums)
 {
     __shared__ float s_view[16], s_proj[16];
-    __shared__ float s_part[PBW_THREADS / 32][NSUMS];
+    constexpr int NS = NSUMS + (RAW ? 4 : 0);
+    __shared__ float s_part[PBW_THREADS / 32][NS];
     if (threadIdx.x < 16) {
         s_view[threadIdx.x] = __ldg(view + threadIdx.x);
         s_proj[threadIdx.x] = __ldg(proj + threadIdx.x);
@@ -44,9 +54,9 @@ preprocess_bwd_kernel(int P, int W, int H,
     __syncthreads();
 
     const int idx = blockIdx.x * PBW_THREADS + threadIdx.x;
-    float sums[NSUMS];
+    float sums[NS];
 #pragma unroll
-    for (int k = 0; k < NSUMS; k++) sums[k] = 0.f;
+    for (int k = 0; k < NS; k++) sums[k] = 0.f;
 
     if (idx < P) {
         float g_mean2D[2] = {0.f, 0.f}, g_col[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, g_op = 0.f;
@@ -69,7 +79,10 @@ preprocess_bwd_kernel(int P, int W, int H,
             // ---- recompute Sigma3D, T, Sigma2D exactly as the forward did ----
             float c3[6];
             float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-            float sx = 0.f, sy = 0.f, sz = 0.f;
+            float sx = 0.f, sy = 0.f, sz = 0.f, raw_norm = 1.f;
+            float act_s[3] = {0.f, 0.f, 0.f};
+            float op_act = 0.f;
+            if (RAW) op_act = act_sigmoid(__ldg(opacities + idx));
             Rot3 R;
             Mat3 M;
             if (cov3D_precomp) {
@@ -77,9 +90,18 @@ preprocess_bwd_kernel(int P, int W, int H,
                 for (int k = 0; k < 6; k++) c3[k] = __ldg(cov3D_precomp + 6 * (size_t)idx + k);
             } else {
                 q = __ldg(rotations + idx);
-                sx = __fmul_rn(scale_modifier, __ldg(scales + 3 * (size_t)idx));
-                sy = __fmul_rn(scale_modifier, __ldg(scales + 3 * (size_t)idx + 1));
-                sz = __fmul_rn(scale_modifier, __ldg(scales + 3 * (size_t)idx + 2));
+                sx = __ldg(scales + 3 * (size_t)idx);
+                sy = __ldg(scales + 3 * (size_t)idx + 1);
+                sz = __ldg(scales + 3 * (size_t)idx + 2);
+                if (RAW) {
+                    sx = expf(sx); sy = expf(sy); sz = expf(sz);
+                    act_s[0] = sx; act_s[1] = sy; act_s[2] = sz;
+                    raw_norm = quat_norm_clamped(q);
+                    q = act_normalize(q, raw_norm);
+                }
+                sx = __fmul_rn(scale_modifier, sx);
+                sy = __fmul_rn(scale_modifier, sy);
+                sz = __fmul_rn(scale_modifier, sz);
                 R = quat_to_R(q.x, q.y, q.z, q.w);
                 M = scale_rot(sx, sy, sz, R);
                 cov3d_from_M(M, c3);
@@ -97,7 +119,7 @@ preprocess_bwd_kernel(int P, int W, int H,
                 const float det_plus = c_xx * c_yy - c_xy * c_xy;
                 const float ratio = det_cov / det_plus;
                 const float h_scale = sqrtf(fmaxf(0.000025f, ratio));
-                const float d_h = g_op * __ldg(opacities + idx);
+                const float d_h = g_op * (RAW ? op_act : __ldg(opacities + idx));
                 g_op = g_op * h_scale;
                 const float d_inside_root = ratio <= 0.000025f ? 0.f : d_h / (2.f * h_scale);
                 const float x = c_xx, y = c_yy, z = c_xy, w = h_var;
@@ -174,13 +196,30 @@ preprocess_bwd_kernel(int P, int W, int H,
                 g_rot.z = 2.f * x * (D[1][0] + D[0][1]) + 2.f * r * (D[2][0] - D[0][2]) + 2.f * z * (D[1][2] + D[2][1]) - 4.f * y * (D[2][2] + D[0][0]);
                 g_rot.w = 2.f * r * (D[0][1] - D[1][0]) + 2.f * x * (D[2][0] + D[0][2]) + 2.f * y * (D[1][2] + D[2][1]) - 4.f * z * (D[1][1] + D[0][0]);
             }
+            if (RAW) {
+                // chain through the activations exactly as autograd does behind the unfused call: the kernel's
+                // dL_dscales (which, like the reference's, is taken w.r.t. mod * s) times d exp(x)/dx = s
+                g_scale[0] *= act_s[0]; g_scale[1] *= act_s[1]; g_scale[2] *= act_s[2];
+                const float qd = q.x * g_rot.x + q.y * g_rot.y + q.z * g_rot.z + q.w * g_rot.w;
+                const float inv_n = 1.f / raw_norm;
+                g_rot = make_float4((g_rot.x - q.x * qd) * inv_n, (g_rot.y - q.y * qd) * inv_n,
+                                    (g_rot.z - q.z * qd) * inv_n, (g_rot.w - q.w * qd) * inv_n);
+                g_op = g_op * op_act * (1.f - op_act);
+                const float g_alt = g_col[3];
+                g_mean3D[0] += __ldg(alt_affine) * g_alt;
+                g_mean3D[1] += __ldg(alt_affine + 1) * g_alt;
+                g_mean3D[2] += __ldg(alt_affine + 2) * g_alt;
+                sums[NSUMS] = mx * g_alt; sums[NSUMS + 1] = my * g_alt; sums[NSUMS + 2] = mz * g_alt; sums[NSUMS + 3] = g_alt;
+                g_col[0] *= SH_C0; g_col[1] *= SH_C0; g_col[2] *= SH_C0;
+            }
         }
 
         dL_dmeans2D[3 * (size_t)idx] = g_mean2D[0];
         dL_dmeans2D[3 * (size_t)idx + 1] = g_mean2D[1];
         dL_dmeans2D[3 * (size_t)idx + 2] = 0.f;
+        constexpr int COUT = RAW ? 3 : C;            // RAW: dL_df_dc [P,3]
 #pragma unroll
-        for (int ch = 0; ch < C; ch++) dL_dcolors[C * (size_t)idx + ch] = g_col[ch];
+        for (int ch = 0; ch < COUT; ch++) dL_dcolors[COUT * (size_t)idx + ch] = g_col[ch];
         dL_dopacity[idx] = g_op;
 #pragma unroll
         for (int k = 0; k < 3; k++) dL_dmeans3D[3 * (size_t)idx + k] = g_mean3D[k];
@@ -198,22 +237,23 @@ preprocess_bwd_kernel(int P, int W, int H,
     // ---- block reduction of the 14 camera sums: shuffle tree, then one atomic per block ----
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < NSUMS; k++) {
+    for (int k = 0; k < NS; k++) {
         float v = sums[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0) s_part[warp][k] = v;
     }
     __syncthreads();
-    if (threadIdx.x < NSUMS) {
+    if (threadIdx.x < NS) {
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < PBW_THREADS / 32; w++) v += s_part[w][threadIdx.x];
-        if (v != 0.f) atomicAdd(cam_sums + threadIdx.x, v);
+        if (v != 0.f) atomicAdd(threadIdx.x < NSUMS ? cam_sums + threadIdx.x : alt_sums + (threadIdx.x - NSUMS), v);
     }
 }
 
-int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels,
+int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels, bool raw_params,
+                          const float* alt_affine, float* alt_sums,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities,
                           const float* view, const float* proj, float scale_modifier,
@@ -223,16 +263,21 @@ int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels,
                           float* dL_drotations, float* cam_sums)
 {
     EOGS_CUDA(cudaMemsetAsync(cam_sums, 0, 16 * sizeof(float), s));
+    if (raw_params) {
+        if (channels != 5 || cov3D_precomp || !alt_affine || !alt_sums) { set_error("the fused-parameter path renders 5 channels from scales+rotations"); return -1; }
+        EOGS_CUDA(cudaMemsetAsync(alt_sums, 0, 4 * sizeof(float), s));
+    }
     const int blocks = (P + PBW_THREADS - 1) / PBW_THREADS;
     auto run = [&](auto kernel) {
         kernel<<<blocks, PBW_THREADS, 0, s>>>(
-            P, W, H, means3D, scales, reinterpret_cast<const float4*>(rotations), cov3D_precomp,
+            P, W, H, alt_affine, alt_sums, means3D, scales, reinterpret_cast<const float4*>(rotations), cov3D_precomp,
             opacities, view, proj, scale_modifier, antialiasing, radii,
             reinterpret_cast<const float4*>(grad_rec), dL_dmeans2D, dL_dcolors, dL_dopacity,
             dL_dmeans3D, dL_dcov3D, dL_dscales, reinterpret_cast<float4*>(dL_drotations), cam_sums);
     };
-    if (channels == 5) run(preprocess_bwd_kernel<5>);
-    else if (channels == 3) run(preprocess_bwd_kernel<3>);
+    if (raw_params) run(preprocess_bwd_kernel<5, true>);
+    else if (channels == 5) run(preprocess_bwd_kernel<5, false>);
+    else if (channels == 3) run(preprocess_bwd_kernel<3, false>);
     else { set_error("channels must be 3 or 5, got %d", channels); return -1; }
     EOGS_LAUNCH_CHECK("preprocess_bwd_kernel");
     return 0;

@@ -51,7 +51,7 @@ extern "C" {
 #define EOGS_API
 #endif
 
-#define EOGS_ABI_VERSION 2
+#define EOGS_ABI_VERSION 3
 #define EOGS_TILE 16            /* BLOCK_X = BLOCK_Y = 16, DGR/cuda_rasterizer/config.h:15-16 */
 #define EOGS_MAX_CHANNELS 5     /* NUM_CHANNELS 5,        DGR/cuda_rasterizer/config.h:14    */
 
@@ -199,6 +199,39 @@ EOGS_API int eogs_backward_band(eogs_stream_t stream, int P, int W, int H, int c
                   float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity,
                   float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
                   float* dL_drotations, float* cam_sums);
+
+/* ---- fused render glue ---------------------------------- */
+/* EOGS++'s render() (gaussian_renderer/renderer.py:84-107) runs ~10 torch kernels before every
+ * rasterizer call and as many after its backward: exp / normalize / sigmoid activations
+ * (scene/gaussian_model.py:41-53,109-137), SH2RGB of the DC coefficients (utils/sh_utils.py:125-126),
+ * the altitude colour A_2 . xyz + b_2 (AffineCamera.ECEF_to_UVA, scene/cameras/affine_cameras.py:
+ * 432-438), a ones column and a concatenation.  These entry points take the RAW parameters of
+ * GaussianModel instead and do all of that inside the geometry kernels, forward and backward:
+ *   xyz [P,3]   log_scales [P,3] (_scaling)   raw_rotations [P,4] (_rotation)
+ *   opacity_logits [P] (_opacity)   features_dc [P,3] (_features_dc)   alt_affine [4] dev = (a, b) of
+ *   altitude = a . xyz + b (column 2 of the camera's transposed `affine`)
+ * and render 5 channels [rgb, altitude, 1].  The render stage is the ordinary
+ * eogs_forward_render_band.  Backward outputs are gradients w.r.t. the raw parameters; alt_sums [4]
+ * = sum_p dL_daltitude_p * (x, y, z, 1), the gradient of the altitude affine row. */
+EOGS_API int eogs_forward_geometry_params_band(eogs_stream_t stream, int P, int W, int H,
+                          int row_begin, int row_end,
+                          const float* xyz, const float* log_scales, const float* raw_rotations,
+                          const float* opacity_logits, const float* features_dc, const float* alt_affine,
+                          const float* viewmatrix, float scale_modifier, int antialiasing,
+                          int32_t* radii, void* geom, eogs_forward_info* info_dev,
+                          eogs_forward_info* info_host);
+EOGS_API int eogs_backward_params_band(eogs_stream_t stream, int P, int W, int H,
+                  int row_begin, int row_end, uint32_t num_instances,
+                  const float* xyz, const float* log_scales, const float* raw_rotations,
+                  const float* opacity_logits, const float* alt_affine,
+                  const float* viewmatrix, const float* projmatrix,
+                  float scale_modifier, int antialiasing, const float* bg,
+                  const int32_t* radii, const void* geom, const uint32_t* point_list,
+                  const void* image, const float* dL_dpix, const float* dL_dinvdepth,
+                  float* grad_scratch,
+                  float* dL_dmeans2D, float* dL_dfeatures_dc, float* dL_dopacity_logits,
+                  float* dL_dxyz, float* dL_dlog_scales, float* dL_draw_rotations,
+                  float* cam_sums, float* alt_sums);
 
 /* ---- markVisible ------------------------------------------------------------------- */
 /* The reference's in_frustum culls nothing for affine cameras (its body is

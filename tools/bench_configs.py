@@ -11,6 +11,9 @@ flushed between reps), instances, and the same workload through the reference's 
   3  1 M Gaussians: main 2048^2 + sun 4096^2 + random 2048^2, fwd+bwd, camera gradients (configs[2])
   5  5 M Gaussians, 8192^2 forward (altitude/DSM), tile bands: 1 GPU = whole image; N GPUs = N bands
      + all-gather                                                        (configs[4])
+  6  the render() glue: one fwd+bwd render of 1 M raw GaussianModel parameters at 2048^2
+     through (a) torch activations + colors_precomp + our rasterizer (what an unchanged renderer.py does) and
+     (b) eogs2_b200.fused.render_fused (activations and chain rules inside the geometry kernels)
 (config 4 = config 3's cameras data-parallel over ranks is what `bench.py --gpus N` measures.)
 """
 import argparse
@@ -197,6 +200,52 @@ def main():
             if rank == 0:
                 print(json.dumps({"config5_checksum": float(color.double().sum().item()),
                                   "alt_checksum": float(color[3].double().abs().sum().item())}), flush=True)
+
+    if 6 in want and world == 1:
+        from types import SimpleNamespace
+        from eogs2_b200 import fused as FU
+        from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+        P6, IMG6 = 1_000_000, 2048
+        sc = S.make_scene(P6, "trained", 1337)
+        C0 = FU.SH_C0
+        raw = dict(xyz=sc.means3D, fdc=((sc.rgb - 0.5) / C0).unsqueeze(1), op=torch.logit(sc.opacities),
+                   sc=torch.log(sc.scales), rot=sc.rotations * 1.7)
+        raw = {k: v.to(dev).requires_grad_(True) for k, v in raw.items()}
+        view = S.make_camera(1337).to(dev).requires_grad_(True)
+        bg = S.background(1337).to(dev)
+        dcol = S.upstream_grads(5, IMG6, IMG6, 1337, False)[0].to(dev)
+        pipe = SimpleNamespace(debug=False, antialiasing=False, compute_cov3D_python=False, require_radii=True)
+        pc = SimpleNamespace(_xyz=raw["xyz"], _features_dc=raw["fdc"], _opacity=raw["op"], _scaling=raw["sc"],
+                             _rotation=raw["rot"], active_sh_degree=0)
+        cam = SimpleNamespace(world_view_transform=view, full_proj_transform=view, affine=view, image_width=IMG6,
+                              image_height=IMG6, FoVx=0.5, FoVy=0.5, camera_center=torch.zeros(3, device=dev),
+                              learn_wv_only_lastparam=False, image_name="synthetic")
+
+        def zero():
+            for t in list(raw.values()) + [view]:
+                t.grad = None
+
+        def glue_unfused():
+            zero()
+            sp = torch.zeros_like(raw["xyz"], requires_grad=True) + 0
+            sp.retain_grad()
+            rs = GaussianRasterizationSettings(IMG6, IMG6, 0.25, 0.25, bg, 1.0, view, view, 0, cam.camera_center,
+                                               False, False, False)
+            rgb = (raw["fdc"] * C0 + 0.5).squeeze(1)
+            alt = (raw["xyz"] @ view[:3, :3] + view[3, :3])[..., 2].unsqueeze(-1)
+            colors = torch.cat([rgb, alt, torch.ones_like(alt)], dim=-1)
+            img, radii, _ = GaussianRasterizer(rs)(
+                means3D=raw["xyz"], means2D=sp, opacities=torch.sigmoid(raw["op"]), colors_precomp=colors,
+                scales=torch.exp(raw["sc"]), rotations=torch.nn.functional.normalize(raw["rot"]))
+            (img * dcol).sum().backward()
+
+        def glue_fused():
+            zero()
+            out = FU.render_fused(cam, pc, pipe, bg)
+            (out["render"] * dcol).sum().backward()
+
+        report("6: 1M, 2048^2 render() fwd+bwd from raw parameters: torch glue + rasterizer vs fused glue (ref_ms = unfused)",
+               timed(glue_fused, args.reps, flush), timed(glue_unfused, args.reps, flush), dict(instances=None))
 
     if args.out and rank == 0:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
