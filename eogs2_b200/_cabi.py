@@ -74,6 +74,10 @@ SIGNATURES = {
         c_ptr, c_ptr, c_ptr, c_ptr, c_f32p, c_f32p,                    # radii, geom, point_list, image, dL_dpix, dL_dinvdepth
         c_f32p,                                                        # grad_scratch
         c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "eogs_resample_forward": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "eogs_resample_backward": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
     "eogs_mark_visible": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_f32p, c_ptr]),
     "eogs_profile_enable": (C.c_int, [C.c_int]),
     "eogs_profile_read": (C.c_int, [c_ptr, C.c_int]),

@@ -233,6 +233,22 @@ EOGS_API int eogs_backward_params_band(eogs_stream_t stream, int P, int W, int H
                   float* dL_dxyz, float* dL_dlog_scales, float* dL_draw_rotations,
                   float* cam_sums, float* alt_sums);
 
+/* ---- virtual-camera resample (sun-view shadow pass) --------- */
+/* render_resample_virtual_camera, steps 2-3 (gaussian_renderer/renderer_cc_shadow.py:32-46):
+ * virtual_uv = (cam2virt @ rendered_uva)[..., :2]; bilinear grid_sample of the virtual camera's render
+ * (align_corners=True, zeros padding) at virtual_uv; altitude = -100 where |u| > 1 or |v| > 1.
+ *   virtual_render [Cv,Hv,Wv] dev (Cv >= 4: rgb, altitude, ...)   cam2virt [3,3] dev row-major
+ *   rendered_uva [H,W,3] dev   ->   out_rgb [3,H,W], out_altitude [H,W], out_uv [H,W,2]
+ * Backward: dL_drgb / dL_daltitude / dL_duv may be NULL (no upstream gradient); dL_dvirtual
+ * [Cv,Hv,Wv] and dL_dcam2virt [9] are zeroed by the call, dL_duva [H,W,3] is written. */
+EOGS_API int eogs_resample_forward(eogs_stream_t stream, int Cv, int Hv, int Wv, int H, int W,
+                                   const float* virtual_render, const float* cam2virt, const float* rendered_uva,
+                                   float* out_rgb, float* out_altitude, float* out_uv);
+EOGS_API int eogs_resample_backward(eogs_stream_t stream, int Cv, int Hv, int Wv, int H, int W,
+                                    const float* virtual_render, const float* cam2virt, const float* rendered_uva,
+                                    const float* dL_drgb, const float* dL_daltitude, const float* dL_duv,
+                                    float* dL_dvirtual, float* dL_duva, float* dL_dcam2virt);
+
 /* ---- markVisible ------------------------------------------------------------------- */
 /* The reference's in_frustum culls nothing for affine cameras (its body is
  * commented out, auxiliary.h:151-176): every Gaussian is reported visible. */

@@ -61,8 +61,11 @@ class FakeCamera:
         self.last_row = (torch.tensor([0.01, -0.02, 0.0, 0.0], device=dev)).requires_grad_(True)
         self.image_name = "synthetic"
 
-    def ECEF_to_UVA(self, xyz):                                    # affine_cameras.py:432-438
-        return xyz @ self.affine[:3, :3] + self.affine[3, :3]
+    def ECEF_to_UVA(self, xyz):                                    # affine_cameras.py:432-438: xyz @ At + bt
+        # written as broadcast multiplies instead of `@`: the same affine map without depending on which cuBLAS
+        # kernel (and internal precision) a [P,3]x[3,3] matmul happens to get on the box
+        At, bt = self.affine[:3, :3], self.affine[3, :3]
+        return xyz[:, 0:1] * At[0] + xyz[:, 1:2] * At[1] + xyz[:, 2:3] * At[2] + bt
 
     def leaves(self):
         return [self.world_view_transform, self.affine, self.last_row]
@@ -114,7 +117,7 @@ def test_fused_render_matches_the_reference_sequence(cuda_dev, P, W, H, seed, aa
     assert got["render"].shape == (5, H, W)
     assert (got["radii"] != ref["radii"]).float().mean().item() <= 1e-4
     err = (got["render"] - ref["render"]).abs()
-    assert (err > 1e-4).float().mean().item() <= 1e-4, float(err.max())
+    assert (err > 1e-4).float().mean().item() <= 1e-4, [float(err[c].max()) for c in range(5)]
     assert got["visibility_filter"].shape[1] == 1
     for name, a, b in zip(("xyz", "features_dc", "opacity", "scaling", "rotation"), pc_f.params(), pc_r.params()):
         assert a.grad is not None and a.grad.shape == b.grad.shape, name
