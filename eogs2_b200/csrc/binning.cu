@@ -233,6 +233,10 @@ int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, c
     uint2* ranges = reinterpret_cast<uint2*>(image + IL.ranges);
     EOGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
     if (I == 0) return 0;
+    if (I > 0x7FFFFFFFu) {        // cub::DeviceRadixSort takes a signed 32-bit item count
+        set_error("%u (Gaussian, tile) instances exceed 2^31-1: render the view in tile bands (eogs_*_band)", I);
+        return -3;
+    }
 
     uint32_t* val_in = reinterpret_cast<uint32_t*>(binning + BL.val_in);
     const int bit = (int)higher_msb(tiles);

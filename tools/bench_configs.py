@@ -14,6 +14,8 @@ flushed between reps), instances, and the same workload through the reference's 
   6  the render() glue: one fwd+bwd render of 1 M raw GaussianModel parameters at 2048^2
      through (a) torch activations + colors_precomp + our rasterizer (what an unchanged renderer.py does) and
      (b) eogs2_b200.fused.render_fused (activations and chain rules inside the geometry kernels)
+  7  the sun-view resample (renderer_cc_shadow.py:32-46) alone, 4096^2 virtual render -> 2048^2 camera frame,
+     fwd+bwd: torch einsum + grid_sample + mask vs eogs2_b200.shadow.resample_virtual
 (config 4 = config 3's cameras data-parallel over ranks is what `bench.py --gpus N` measures.)
 """
 import argparse
@@ -246,6 +248,35 @@ def main():
 
         report("6: 1M, 2048^2 render() fwd+bwd from raw parameters: torch glue + rasterizer vs fused glue (ref_ms = unfused)",
                timed(glue_fused, args.reps, flush), timed(glue_unfused, args.reps, flush), dict(instances=None))
+
+    if 7 in want and world == 1:
+        from eogs2_b200 import shadow as SHD
+        Hc = Wc = 2048
+        g = torch.Generator().manual_seed(7)
+        virt = torch.randn(5, 2 * Hc, 2 * Wc, generator=g).to(dev).requires_grad_(True)
+        u, v = torch.meshgrid(torch.linspace(-1, 1, Wc), torch.linspace(-1, 1, Hc), indexing="xy")
+        uva = torch.stack([u, v, torch.rand(Hc, Wc, generator=g) * 60 - 20], -1).to(dev).requires_grad_(True)
+        M = torch.tensor([[0.5, 0.0, -0.0015], [0.0, 0.5, -0.00125], [0.0, 0.0, 1.0]], device=dev).requires_grad_(True)
+        w_rgb = torch.randn(3, Hc, Wc, generator=g).to(dev)
+        w_alt = torch.randn(Hc, Wc, generator=g).to(dev)
+
+        def torch_path():
+            for t in (virt, uva, M):
+                t.grad = None
+            uv = torch.einsum("...ij,...j->...i", M, uva)[..., :2]
+            smp = torch.nn.functional.grid_sample(virt.unsqueeze(0), uv.unsqueeze(0), align_corners=True).squeeze(0)
+            alt = smp[3]
+            alt[(uv.abs() > 1).any(-1)] = -100
+            ((smp[:3] * w_rgb).sum() + (alt * w_alt).sum()).backward()
+
+        def fused_path():
+            for t in (virt, uva, M):
+                t.grad = None
+            rgb, alt, uv = SHD.resample_virtual(virt, M, uva)
+            ((rgb * w_rgb).sum() + (alt * w_alt).sum()).backward()
+
+        report("7: sun-view resample 4096^2 -> 2048^2 fwd+bwd: torch einsum+grid_sample+mask vs fused kernel (ref_ms = torch)",
+               timed(fused_path, args.reps, flush), timed(torch_path, args.reps, flush), dict(instances=None))
 
     if args.out and rank == 0:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
