@@ -78,6 +78,10 @@ SIGNATURES = {
                                         c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
     "eogs_resample_backward": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "eogs_photometric_forward": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                           c_f32p, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p]),
+    "eogs_photometric_backward": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                            c_f32p, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p]),
     "eogs_mark_visible": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_f32p, c_ptr]),
     "eogs_profile_enable": (C.c_int, [C.c_int]),
     "eogs_profile_read": (C.c_int, [c_ptr, C.c_int]),

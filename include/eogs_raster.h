@@ -249,6 +249,21 @@ EOGS_API int eogs_resample_backward(eogs_stream_t stream, int Cv, int Hv, int Wv
                                     const float* dL_drgb, const float* dL_daltitude, const float* dL_duv,
                                     float* dL_dvirtual, float* dL_duva, float* dL_dcam2virt);
 
+/* ---- photometric loss --------------------------------------- */
+/* L = (1 - lambda) * mean|image - gt| + lambda * (1 - SSIM(image, gt))   (loss/shadow.py:21-29 with
+ * l1_loss / ssim of utils/loss_utils.py:18-85: 11x11 Gaussian window, sigma 1.5, zero padding).
+ *   window11 [11] HOST floats: the normalised 1-D window (gaussian(11, 1.5))
+ *   image, gt [C,H,W] dev      maps [3,C,H,W] dev: per-pixel partials kept for the backward
+ *   sums2 [2] dev scratch      out3 [3] dev: {loss, mean SSIM, mean L1}
+ * Backward: dL_dloss [1] dev or NULL (= 1); dL_dimage [C,H,W] dev is written in the planar layout the
+ * rasterizer's backward consumes. */
+EOGS_API int eogs_photometric_forward(eogs_stream_t stream, int C, int H, int W, const float* window11,
+                                      const float* image, const float* gt, float lambda_dssim,
+                                      float* maps, float* sums2, float* out3);
+EOGS_API int eogs_photometric_backward(eogs_stream_t stream, int C, int H, int W, const float* window11,
+                                       const float* image, const float* gt, float lambda_dssim,
+                                       const float* maps, const float* dL_dloss, float* dL_dimage);
+
 /* ---- markVisible ------------------------------------------------------------------- */
 /* The reference's in_frustum culls nothing for affine cameras (its body is
  * commented out, auxiliary.h:151-176): every Gaussian is reported visible. */

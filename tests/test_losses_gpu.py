@@ -1,0 +1,70 @@
+"""GPU: the fused photometric loss (eogs2_b200/losses.py, csrc/ssim_loss.cu) against the reference's torch
+formulation (utils/loss_utils.py:18-85, loss/shadow.py:21-29), restated below line by line.
+Bars: loss value 1e-5 relative, gradient 1e-4 relative (the reference's 2-D window is the rounded outer product
+of the 1-D window; the kernel applies the 1-D window twice)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from eogs2_b200 import losses as L
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_ssim(img1, img2, window_size=11):
+    channel = img1.size(-3)
+    w1 = L.gaussian_window(window_size, 1.5).unsqueeze(1)
+    window = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0).expand(channel, 1, window_size, window_size).contiguous()
+    window = window.to(img1.device).type_as(img1)
+    pad = window_size // 2
+    mu1 = F.conv2d(img1, window, padding=pad, groups=channel)
+    mu2 = F.conv2d(img2, window, padding=pad, groups=channel)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    sigma1_sq = F.conv2d(img1 * img1, window, padding=pad, groups=channel) - mu1_sq
+    sigma2_sq = F.conv2d(img2 * img2, window, padding=pad, groups=channel) - mu2_sq
+    sigma12 = F.conv2d(img1 * img2, window, padding=pad, groups=channel) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    ssim_map = ((2 * mu1_mu2 + C1) * (2 * sigma12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2))
+    return ssim_map.mean()
+
+
+def ref_photometric(image, gt, lam):
+    Ll1 = torch.abs(image - gt).mean()
+    return (1.0 - lam) * Ll1 + lam * (1.0 - ref_ssim(image, gt))
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu().numpy(), b.detach().double().cpu().numpy()
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+@pytest.mark.parametrize("C,H,W,lam,seed", [(3, 128, 160, 0.2, 1), (1, 67, 45, 0.2, 2), (3, 16, 16, 1.0, 3),
+                                            (5, 40, 300, 0.0, 4), (3, 512, 512, 0.2, 5)])
+def test_photometric_loss_matches_torch(cuda_dev, C, H, W, lam, seed):
+    g = torch.Generator().manual_seed(seed)
+    gt = torch.rand(C, H, W, generator=g).to(cuda_dev)
+    base = (gt.cpu() + 0.15 * torch.randn(C, H, W, generator=g)).clamp(0, 1).to(cuda_dev)
+    base[:, : H // 4] = gt[:, : H // 4]                     # a region with image == gt: |.|' = 0 there
+    a = base.clone().requires_grad_(True)
+    b = base.clone().requires_grad_(True)
+    up = 1.7
+    loss_ref = ref_photometric(a, gt, lam)
+    (loss_ref * up).backward()
+    loss, ssim_mean, l1_mean = L.photometric_loss(b, gt, lam, return_parts=True)
+    (loss * up).backward()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-5 * max(1.0, abs(float(loss_ref.detach())))
+    assert abs(float(l1_mean) - float(torch.abs(base - gt).mean())) <= 1e-6
+    assert abs(float(ssim_mean) - float(ref_ssim(base, gt))) <= 1e-5
+    assert b.grad.shape == a.grad.shape and rel(b.grad, a.grad) < 1e-4, rel(b.grad, a.grad)
+
+
+def test_module_and_helpers(cuda_dev):
+    g = torch.Generator().manual_seed(9)
+    gt = torch.rand(3, 48, 64, generator=g).to(cuda_dev)
+    img = torch.rand(3, 48, 64, generator=g).to(cuda_dev)
+    assert abs(float(L.photometric_L(0.2)(img, gt, None)) - float(ref_photometric(img, gt, 0.2))) < 1e-5
+    assert abs(float(L.l1_loss(img, gt)) - float(torch.abs(img - gt).mean())) < 1e-6
+    assert abs(float(L.ssim(img, gt)) - float(ref_ssim(img, gt))) < 1e-5
+    with pytest.raises(Exception):
+        L.photometric_loss(img.cpu(), gt.cpu())

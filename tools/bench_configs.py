@@ -16,6 +16,8 @@ flushed between reps), instances, and the same workload through the reference's 
      (b) eogs2_b200.fused.render_fused (activations and chain rules inside the geometry kernels)
   7  the sun-view resample (renderer_cc_shadow.py:32-46) alone, 4096^2 virtual render -> 2048^2 camera frame,
      fwd+bwd: torch einsum + grid_sample + mask vs eogs2_b200.shadow.resample_virtual
+  8  the photometric loss (loss/shadow.py:21-29) on a 3 x 2048^2 image, fwd+bwd: torch l1 + 5 x conv2d SSIM vs
+     eogs2_b200.losses.photometric_loss
 (config 4 = config 3's cameras data-parallel over ranks is what `bench.py --gpus N` measures.)
 """
 import argparse
@@ -277,6 +279,31 @@ def main():
 
         report("7: sun-view resample 4096^2 -> 2048^2 fwd+bwd: torch einsum+grid_sample+mask vs fused kernel (ref_ms = torch)",
                timed(fused_path, args.reps, flush), timed(torch_path, args.reps, flush), dict(instances=None))
+
+    if 8 in want and world == 1:
+        import torch.nn.functional as TF
+        from eogs2_b200 import losses as LS
+        g = torch.Generator().manual_seed(8)
+        gt = torch.rand(3, 2048, 2048, generator=g).to(dev)
+        img = (gt + 0.1 * torch.randn(3, 2048, 2048, generator=g).to(dev)).clamp(0, 1).requires_grad_(True)
+        w1 = LS.gaussian_window().unsqueeze(1)
+        window = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0).expand(3, 1, 11, 11).contiguous().to(dev)
+
+        def torch_loss():
+            img.grad = None
+            conv = lambda x: TF.conv2d(x, window, padding=5, groups=3)
+            mu1, mu2 = conv(img), conv(gt)
+            mu1_sq, mu2_sq, mu12 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+            s1, s2, s12 = conv(img * img) - mu1_sq, conv(gt * gt) - mu2_sq, conv(img * gt) - mu12
+            ssim_map = ((2 * mu12 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1_sq + mu2_sq + 1e-4) * (s1 + s2 + 9e-4))
+            (0.8 * torch.abs(img - gt).mean() + 0.2 * (1.0 - ssim_map.mean())).backward()
+
+        def fused_loss():
+            img.grad = None
+            LS.photometric_loss(img, gt, 0.2).backward()
+
+        report("8: photometric loss 3x2048^2 fwd+bwd: torch L1 + conv2d SSIM vs fused kernels (ref_ms = torch)",
+               timed(fused_loss, args.reps, flush), timed(torch_loss, args.reps, flush), dict(instances=None))
 
     if args.out and rank == 0:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
