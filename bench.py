@@ -144,6 +144,42 @@ def ours_step_factory(wl, dev):
     return step
 
 
+def iteration_factory(wl, dev, rank, impl):
+    """BASELINE metric, second half ("ms/iter"): the EOGS++ steady-state iteration pattern of ONE camera
+    (train_pan.py:278,305-316,375-391) = main W x H + sun 2W x 2H + random-camera W x H
+    renders, forward + backward each, same 1 M Gaussians; losses / optimiser excluded."""
+    from eogs2_b200 import scene as S
+    sc, d = wl["sc"], wl["dev"]
+    empty = torch.empty(0, device=dev)
+    campos = torch.zeros(3, device=dev)
+    cam = wl["view_host"]
+    specs = [(cam, IMG, IMG), (S.sun_camera(cam), 2 * IMG, 2 * IMG), (S.random_camera(cam, 0.01, SEED + rank), IMG, IMG)]
+    views = []
+    for k, (v, Wv, Hv) in enumerate(specs):
+        dcol, dinv = S.upstream_grads(5, Hv, Wv, SEED + 10 * rank + k, False)
+        views.append(dict(view=v.to(dev), colors=S.colors_precomp(sc, v).to(dev), W=Wv, H=Hv, dcol=dcol.to(dev),
+                          dinv=dinv.to(dev)))
+    if impl == "ours":
+        import eogs2_b200 as E
+
+        def it():
+            for v in views:
+                st = E.rasterize_forward_raw(wl["bg"], d["means3D"], v["colors"], d["opacities"], d["scales"],
+                                             d["rotations"], 1.0, empty, v["view"], v["H"], v["W"], False, False)
+                E.rasterize_backward_raw(st, wl["bg"], d["means3D"], v["colors"], d["opacities"], d["scales"],
+                                         d["rotations"], 1.0, empty, v["view"], v["view"], v["dcol"], v["dinv"])
+    else:
+        from oracle import ref_rasterizer as R
+
+        def it():
+            for v in views:
+                st = R.forward(wl["bg"], d["means3D"], v["colors"], d["opacities"], d["scales"], d["rotations"], 1.0,
+                               empty, v["view"], v["view"], 1.0, 1.0, v["H"], v["W"], campos, False, False)
+                R.backward(st, wl["bg"], d["means3D"], v["colors"], d["opacities"], d["scales"], d["rotations"], 1.0,
+                           empty, v["view"], v["view"], 1.0, 1.0, v["dcol"], v["dinv"], campos, False)
+    return it
+
+
 def ours_e2e_factory(wl, dev, world=1):
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     h = wl["host"]
@@ -345,6 +381,8 @@ def main():
         total_ms, wall = timed_steps(step, args.steps, args.warmup, flush, 1)
         e2e_step, h2d, d2h = ref_e2e_factory(wl, dev)
         e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, 1)
+        it_steps = max(3, min(args.steps, 5))
+        iter_ms, _ = timed_steps(iteration_factory(wl, dev, 0, "reference"), it_steps, 3, flush, 1)
         clocks = sampler.stop()
         st, _ = step()
         val = args.steps / (total_ms / 1e3)
@@ -355,6 +393,7 @@ def main():
                     cpu_baseline={"value": val, "unit": "renders/s", "cores": 0, "kind": "reference",
                                   "sample": "full workload; the reference has no CPU backend, so this arm runs its own CUDA "
                                             "kernels (DGR cuda_rasterizer, compiled for sm_100a with nvcc defaults) on the GPU"},
+                    iter_ms=iter_ms / it_steps,
                     instances=st.num_rendered, requested_gpus=ref_world)
         print(json.dumps(line))
         return 0
@@ -420,6 +459,10 @@ def main():
     if not args.no_e2e:
         e2e_ms, _ = timed_steps(e2e_step, args.steps, args.warmup, flush, world)
 
+    # "ms/iter": main + sun@2x + random renders fwd+bwd per rank (+ the gradient all-reduce at N > 1), max over ranks
+    it_steps = max(3, min(args.steps, 10))
+    iter_ms, _ = timed_steps(iteration_factory(wl, dev, rank, "ours"), it_steps, 3, flush, world, post)
+
     value = world * args.steps / (total_ms / 1e3)
     # roofline of the dominant kernel: blend backward.  Algorithmic bytes per launch:
     # per instance 4 B id + 48 B record gathered + 44 B (11 floats) reduced into the gradient record;
@@ -446,6 +489,9 @@ def main():
                                   "reported because the contract asks for it, the binding ceiling is the issue rate "
                                   "(DESIGN.md §4)"},
                 stage_ms={STAGES[i]: round(stage_ms[i], 4) for i in range(1, len(STAGES))},
+                iter_ms=iter_ms / it_steps,
+                iter_pattern="one camera per rank: main 2048^2 + sun 4096^2 + random 2048^2, fwd+bwd each"
+                             + (", then the gradient all-reduce" if world > 1 else ""),
                 instances=I, wall_s=wall)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
