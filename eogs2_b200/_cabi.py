@@ -82,6 +82,11 @@ SIGNATURES = {
                                            c_f32p, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p]),
     "eogs_photometric_backward": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                             c_f32p, c_f32p, C.c_float, c_f32p, c_f32p, c_f32p]),
+    "eogs_adam_step": (C.c_int, [c_ptr, C.c_ulonglong, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_float),
+                                 C.c_double, C.c_double, C.c_double, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "eogs_prune_temp_bytes": (C.c_size_t, [C.c_int]),
+    "eogs_prune_offsets": (C.c_int, [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "eogs_prune_gather": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_f32p, c_f32p]),
     "eogs_mark_visible": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_f32p, c_ptr]),
     "eogs_profile_enable": (C.c_int, [C.c_int]),
     "eogs_profile_read": (C.c_int, [c_ptr, C.c_int]),

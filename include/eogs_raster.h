@@ -264,6 +264,26 @@ EOGS_API int eogs_photometric_backward(eogs_stream_t stream, int C, int H, int W
                                        const float* image, const float* gt, float lambda_dssim,
                                        const float* maps, const float* dL_dloss, float* dL_dimage);
 
+/* ---- replicated optimiser step and prune compaction --------- */
+/* Adam of all parameter groups in one launch over a flat fp32 buffer split into `num_segments` contiguous
+ * segments (GaussianModel.training_setup, scene/gaussian_model.py:223-271: one group per parameter, eps 1e-15).
+ *   segment_end [num_segments] HOST: exclusive end offset of each segment (last = n); lr [num_segments] HOST
+ *   step: 1-based step count (bias corrections are computed in double on the host, like torch)
+ *   params / exp_avg / exp_avg_sq [n] dev are updated in place; grads [n] dev (e.g. the all-reduced bucket). */
+EOGS_API int eogs_adam_step(eogs_stream_t stream, unsigned long long n, int num_segments,
+                            const unsigned long long* segment_end, const float* lr,
+                            double beta1, double beta2, double eps, int step,
+                            float* params, const float* grads, float* exp_avg, float* exp_avg_sq);
+/* Prune compaction (prune_points / _prune_optimizer, scene/gaussian_model.py:466-505):
+ *   eogs_prune_offsets: exclusive scan of keep[P] (u8) -> offsets[P] (destination row of every kept row),
+ *                       *count_dev = number of kept rows; temp: eogs_prune_temp_bytes(P) bytes of scratch.
+ *   eogs_prune_gather:  dst[offsets[r], :] = src[r, :] for kept rows of a [P, width] fp32 array. */
+EOGS_API size_t eogs_prune_temp_bytes(int P);
+EOGS_API int eogs_prune_offsets(eogs_stream_t stream, int P, const uint8_t* keep, uint32_t* offsets,
+                                void* temp, size_t temp_bytes, uint32_t* count_dev);
+EOGS_API int eogs_prune_gather(eogs_stream_t stream, int P, int width, const uint8_t* keep,
+                               const uint32_t* offsets, const float* src, float* dst);
+
 /* ---- markVisible ------------------------------------------------------------------- */
 /* The reference's in_frustum culls nothing for affine cameras (its body is
  * commented out, auxiliary.h:151-176): every Gaussian is reported visible. */
