@@ -18,6 +18,9 @@ flushed between reps), instances, and the same workload through the reference's 
      fwd+bwd: torch einsum + grid_sample + mask vs eogs2_b200.shadow.resample_virtual
   8  the photometric loss (loss/shadow.py:21-29) on a 3 x 2048^2 image, fwd+bwd: torch l1 + 5 x conv2d SSIM vs
      eogs2_b200.losses.photometric_loss
+  9  one full camera iteration at 1 M Gaussians, 2048^2 (main render + sun render at 4096^2 + resample + shading +
+     photometric loss + backward + Adam): the reference's torch stages on our rasterizer vs everything fused
+     (eogs2_b200/iteration.py)
 (config 4 = config 3's cameras data-parallel over ranks is what `bench.py --gpus N` measures.)
 """
 import argparse
@@ -304,6 +307,40 @@ def main():
 
         report("8: photometric loss 3x2048^2 fwd+bwd: torch L1 + conv2d SSIM vs fused kernels (ref_ms = torch)",
                timed(fused_loss, args.reps, flush), timed(torch_loss, args.reps, flush), dict(instances=None))
+
+    if 9 in want and world == 1:
+        from types import SimpleNamespace
+        sys.path.insert(0, str(ROOT / "tests"))
+        import iteration_ref as IR
+        from eogs2_b200 import iteration as ITR
+        from eogs2_b200 import optim as OPT
+        P9, IMG9 = 1_000_000, 2048
+        lrs = {"xyz": 1.6e-4, "f_dc": 2.5e-3, "opacity": 5e-2, "scaling": 5e-3, "rotation": 1e-3}
+        pipe = SimpleNamespace(debug=False, antialiasing=False, compute_cov3D_python=False, require_radii=False)
+        bg = S.background(9).to(dev)
+        cam, sun, cam2sun = IR.make_cameras(dev, 1337, IMG9, IMG9)
+        init = IR.raw_params(dev, P9, 1337)
+        gt = torch.rand(3, IMG9, IMG9, generator=torch.Generator().manual_seed(9)).to(dev)
+        ref_p = {n: torch.nn.Parameter(p.clone()) for n, p in init.items()}
+        ref_opt = torch.optim.Adam([{"params": [ref_p[n]], "lr": lrs[n], "name": n} for n in ref_p], lr=0.0, eps=1e-15)
+        opt = OPT.FlatGaussianAdam(init, lrs)
+
+        def torch_iter():
+            ref_opt.zero_grad(set_to_none=True)
+            loss, _ = ITR.camera_iteration(cam, sun, cam2sun, ITR.model_view(ref_p), pipe, bg, gt, render_fn=IR.torch_render,
+                                           resample_fn=IR.torch_resample, loss_fn=IR.torch_photometric)
+            loss.backward()
+            ref_opt.step()
+
+        def fused_iter():
+            opt.zero_grad()
+            loss, _ = ITR.camera_iteration(cam, sun, cam2sun, ITR.model_view(opt.params), pipe, bg, gt)
+            loss.backward()
+            opt.step()
+
+        report("9: full camera iteration 1M, 2048^2 (main + sun@2x renders, resample, shading, L1+DSSIM, backward, Adam): "
+               "torch stages on our rasterizer vs all fused (ref_ms = torch stages)",
+               timed(fused_iter, args.reps, flush), timed(torch_iter, args.reps, flush), dict(instances=None))
 
     if args.out and rank == 0:
         Path(args.out).parent.mkdir(parents=True, exist_ok=True)
