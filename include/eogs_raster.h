@@ -51,7 +51,7 @@ extern "C" {
 #define EOGS_API
 #endif
 
-#define EOGS_ABI_VERSION 3
+#define EOGS_ABI_VERSION 4
 #define EOGS_TILE 16            /* BLOCK_X = BLOCK_Y = 16, DGR/cuda_rasterizer/config.h:15-16 */
 #define EOGS_MAX_CHANNELS 5     /* NUM_CHANNELS 5,        DGR/cuda_rasterizer/config.h:14    */
 
@@ -283,6 +283,27 @@ EOGS_API int eogs_prune_offsets(eogs_stream_t stream, int P, const uint8_t* keep
                                 void* temp, size_t temp_bytes, uint32_t* count_dev);
 EOGS_API int eogs_prune_gather(eogs_stream_t stream, int P, int width, const uint8_t* keep,
                                const uint32_t* offsets, const float* src, float* dst);
+
+/* ---- simple-knn distCUDA2 ------------------------------------ */
+/* distCUDA2 (submodules/simple-knn/spatial.cu:15-26 -> SimpleKNN::knn, simple_knn.cu:187-222): for every point the
+ * mean of the squared distances to its 3 nearest neighbours (other indices; duplicates count with distance 0;
+ * missing neighbours count as 1e37 like the reference's FLT_MAX).  Bit-exact against the reference: same
+ * per-pair expression fma(dz,dz,fma(dx,dx,dy*dy)) and ((b0+b1)+b2)/3.  Finite inputs.
+ *   points [P,3] dev fp32   scratch: eogs_knn_bytes(P) bytes dev   mean_dist2 [P] dev fp32
+ * Stream-ordered, no host synchronisation (the reference blocks twice on D2H copies of the bounding box). */
+EOGS_API size_t eogs_knn_bytes(int P);
+EOGS_API int eogs_knn_dist2(eogs_stream_t stream, int P, const float* points, void* scratch, size_t scratch_bytes,
+                            float* mean_dist2);
+
+/* ---- DSM splat ------------------------------------------------ */
+/* The `plyflatten(cloud, xoff, yoff, resolution, xsize, ysize, radius, sigma)` call of compute_dsm_from_view
+ * (utils/dsm_utils.py:27-37): every point (x, y, v) is averaged, with weight exp(-dist^2 / (2 sigma^2)), into
+ * the raster cells within `radius` cells of its own; unreached cells are NaN.
+ *   cloud [N,3] dev fp64 (x, y, value)   accum [2*xsize*ysize] dev fp64 scratch (zeroed by the call)
+ *   raster [ysize, xsize] dev fp32 (the [:, :, 0] plane of plyflatten's result) */
+EOGS_API int eogs_dsm_splat(eogs_stream_t stream, long long N, const double* cloud, double xoff, double yoff,
+                            double resolution, int xsize, int ysize, int radius, float sigma,
+                            double* accum, float* raster);
 
 /* ---- markVisible ------------------------------------------------------------------- */
 /* The reference's in_frustum culls nothing for affine cameras (its body is

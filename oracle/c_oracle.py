@@ -138,3 +138,23 @@ def grad_viewmatrix(dL_dT, dL_dmeans2D, means3D, W, H) -> np.ndarray:
     g[:3, :3] += means3D.astype(np.float64).T @ dL_dmeans2D.astype(np.float64)
     g[-1, :3] += dL_dmeans2D.astype(np.float64).sum(0)
     return g
+
+
+def dist2(points) -> np.ndarray:
+    """distCUDA2 (simple-knn spatial.cu:15-26) by brute force: O(P^2), keep P in the tens of thousands."""
+    lib = load()
+    pts = _f32(points).reshape(-1, 3)
+    out = np.zeros(pts.shape[0], np.float32)
+    lib.oracle_dist2(C.c_int(pts.shape[0]), _p(pts), _p(out))
+    return out
+
+
+def plyflatten(cloud, xoff, yoff, resolution, xsize, ysize, radius, sigma) -> np.ndarray:
+    """plyflatten(...) as called by utils/dsm_utils.py:28-37 -> [ysize, xsize, 1] float32.  PARITY UNPINNED
+    (the package is absent; see the header of eogs_oracle.c)."""
+    lib = load()
+    c = np.ascontiguousarray(np.asarray(cloud, dtype=np.float64)).reshape(-1, 3)
+    out = np.zeros((ysize, xsize, 1), np.float32)
+    lib.oracle_plyflatten(C.c_longlong(c.shape[0]), _p(c), C.c_double(xoff), C.c_double(yoff), C.c_double(resolution),
+                          C.c_int(xsize), C.c_int(ysize), C.c_int(radius), C.c_float(sigma), _p(out))
+    return out

@@ -16,6 +16,13 @@
  *   oracle_pre_bwd      backward.cu:147-327 (computeCov2DCUDA), :400-454 (preprocessCUDA bwd),
  *                       :331-394 (computeCov3D bwd); the dL_dT output uses the INTENDED stride
  *                       6*idx+k (the reference writes idx+k, a data race, backward.cu:320-325)
+ *   oracle_dist2        submodules/simple-knn/simple_knn.cu:118-185 (updateKBest<3>, boxMeanDist) and
+ *                       spatial.cu:15-26 (distCUDA2): brute force over all j != i — the reference's
+ *                       Morton boxes only prune an exact search (pinned by tests/golden/ref_knn.npz)
+ *   oracle_plyflatten   the `plyflatten` call of utils/dsm_utils.py:27-37.  PARITY UNPINNED: plyflatten is a
+ *                       third-party dependency (requirements.txt:18, no version pin) that is absent from
+ *                       /root/reference and from this image; this restates its published algorithm
+ *                       (plyflatten.c, rasterize_cloud) from the documentation of its behaviour
  *
  * Bit-exactness: everything that feeds the sort keys and tile ranges (means2D, radius, rect,
  * depth) is computed with the exact FMA/mul/add sequence that nvcc 12.9 emitted for the
@@ -453,4 +460,67 @@ uint32_t oracle_higher_msb(uint32_t n) {        /* getHigherMsb, rasterizer_impl
     while (step > 1) { step /= 2; if (n >> msb) msb += step; else msb -= step; }
     if (n >> msb) msb++;
     return msb;
+}
+
+/* ---- distCUDA2: mean squared distance to the 3 nearest neighbours --------------------------------
+ * simple_knn.cu:118-132 (updateKBest<3>): d = p_j - p_i; dist = d.x*d.x + d.y*d.y + d.z*d.z, which nvcc
+ * contracts to fma(d.z,d.z, fma(d.x,d.x, d.y*d.y)) (SASS of boxMeanDist for sm_100a: FMUL on y, FFMA on x, FFMA on z);
+ * sorted insertion with strict '>' comparisons.  :173-184: every j != i is a candidate (`if (i == idx)
+ * continue;`), boxes are skipped only when they cannot hold a closer point, so the result is the exact
+ * 3-NN.  :185: dists = (best[0] + best[1] + best[2]) / 3.0f, left to right.  :26: FLT_MAX is 1E+37. */
+void oracle_dist2(int P, const float* pts, float* out)
+{
+    for (int i = 0; i < P; i++) {
+        const float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+        float best[3] = { 1e37f, 1e37f, 1e37f };
+        for (int j = 0; j < P; j++) {
+            if (j == i) continue;
+            const float dx = pts[3 * j] - x, dy = pts[3 * j + 1] - y, dz = pts[3 * j + 2] - z;
+            float dist = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+            for (int k = 0; k < 3; k++) {
+                if (best[k] > dist) { float t = best[k]; best[k] = dist; dist = t; }
+            }
+        }
+        out[i] = ((best[0] + best[1]) + best[2]) / 3.0f;
+    }
+}
+
+/* ---- plyflatten (PARITY UNPINNED, see the header) ------------------------------------------------
+ * rasterize_cloud of the `plyflatten` package as called by utils/dsm_utils.py:28-37 with one value column:
+ * sequential weighted running average per cell, fp32 accumulators, NaN where no point landed. */
+static int ply_rescale(double x, double mn, double mx, int w, int* inside)
+{
+    int r = (int)(w * (x - mn) / (mx - mn));
+    *inside = r >= 0 && r < w;
+    return r;
+}
+
+void oracle_plyflatten(long long N, const double* cloud, double xoff, double yoff, double resolution,
+                       int w, int h, int radius, float sigma, float* raster)
+{
+    float* cnt = (float*)calloc((size_t)w * h, sizeof(float));
+    float* avg = (float*)calloc((size_t)w * h, sizeof(float));
+    const double sigma2mult2 = 2.0 * (double)sigma * (double)sigma;
+    for (long long k = 0; k < N; k++) {
+        const double xx = cloud[3 * k], yy = cloud[3 * k + 1];
+        const float v = (float)cloud[3 * k + 2];
+        int in_x, in_y;
+        const int i = ply_rescale(xx, xoff, xoff + w * resolution, w, &in_x);
+        const int j = ply_rescale(-yy, -yoff, -yoff + h * resolution, h, &in_y);
+        if (!in_x || !in_y) continue;
+        for (int k1 = -radius; k1 <= radius; k1++)
+            for (int k2 = -radius; k2 <= radius; k2++) {
+                const int ii = i + k1, jj = j + k2;
+                if (ii < 0 || ii >= w || jj < 0 || jj >= h) continue;
+                const float dist_x = (float)(xx - (xoff + resolution * (0.5 + ii)));
+                const float dist_y = (float)(yy - (yoff - resolution * (0.5 + jj)));
+                const float dist = hypotf(dist_x, dist_y);
+                const float weight = (float)exp(-(double)(dist * dist) / sigma2mult2);
+                const size_t c = (size_t)jj * w + ii;
+                avg[c] = (v * weight + cnt[c] * avg[c]) / (weight + cnt[c]);
+                cnt[c] += weight;
+            }
+    }
+    for (size_t c = 0; c < (size_t)w * h; c++) raster[c] = cnt[c] != 0.f ? avg[c] : NAN;
+    free(cnt); free(avg);
 }
