@@ -18,7 +18,7 @@
  *                       6*idx+k (the reference writes idx+k, a data race, backward.cu:320-325)
  *   oracle_dist2        submodules/simple-knn/simple_knn.cu:118-185 (updateKBest<3>, boxMeanDist) and
  *                       spatial.cu:15-26 (distCUDA2): brute force over all j != i — the reference's
- *                       Morton boxes only prune an exact search (pinned by tests/golden/ref_knn.npz)
+ *                       Morton boxes only prune an exact search (pinned by tests/golden/knn_ref.npz)
  *   oracle_plyflatten   the `plyflatten` call of utils/dsm_utils.py:27-37.  PARITY UNPINNED: plyflatten is a
  *                       third-party dependency (requirements.txt:18, no version pin) that is absent from
  *                       /root/reference and from this image; this restates its published algorithm

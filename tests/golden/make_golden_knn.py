@@ -1,8 +1,8 @@
-"""Generates tests/golden/ref_knn.npz by running the REFERENCE simple-knn (oracle/_ref/libknn_ref.so, built
+"""Generates tests/golden/knn_ref.npz by running the REFERENCE simple-knn (oracle/_ref/libknn_ref.so, built
 from /root/reference by oracle/ref_build/Makefile) on a B200:
 
-    gpurun -- python tests/golden/make_golden_knn.py     # writes gpurun_out/golden/ref_knn.npz
-    cp gpurun_out/golden/ref_knn.npz tests/golden/
+    gpurun -- python tests/golden/make_golden_knn.py     # writes gpurun_out/golden/knn_ref.npz
+    cp gpurun_out/golden/knn_ref.npz tests/golden/
 
 The reference ships no test of distCUDA2; this fixture pins oracle_dist2 (oracle/eogs_oracle.c, CPU test,
 bit-exact) and the CUDA path (GPU test, bit-exact).  Inputs are stored next to the outputs.
@@ -29,7 +29,7 @@ def main():
         d = ref_knn.distCUDA2(torch.from_numpy(p).cuda()).cpu().numpy()
         save[f"{name}_points"], save[f"{name}_dist2"] = p, d
         print(name, P, d[:3])
-    np.savez_compressed(out_dir / "ref_knn.npz", **save)
+    np.savez_compressed(out_dir / "knn_ref.npz", **save)
 
 
 if __name__ == "__main__":

@@ -1,5 +1,5 @@
 """CPU: the distCUDA2 oracle (oracle/eogs_oracle.c: oracle_dist2) reproduces the reference's outputs
-(tests/golden/ref_knn.npz, made by tests/golden/make_golden_knn.py with the compiled reference on a B200)
+(tests/golden/knn_ref.npz, made by tests/golden/make_golden_knn.py with the compiled reference on a B200)
 bit for bit; the host mirror has the reference's import path and refuses CPU tensors."""
 from pathlib import Path
 
@@ -10,7 +10,7 @@ import torch
 from knn_cases import GOLDEN_CASES, points
 from oracle import c_oracle as O
 
-GOLDEN = Path(__file__).resolve().parent / "golden" / "ref_knn.npz"
+GOLDEN = Path(__file__).resolve().parent / "golden" / "knn_ref.npz"
 
 
 @pytest.mark.parametrize("name", sorted(GOLDEN_CASES))

@@ -11,7 +11,7 @@ from oracle import c_oracle as O
 from oracle import ref_knn
 
 pytestmark = pytest.mark.gpu
-GOLDEN = Path(__file__).resolve().parent / "golden" / "ref_knn.npz"
+GOLDEN = Path(__file__).resolve().parent / "golden" / "knn_ref.npz"
 
 
 def ours(p: np.ndarray) -> np.ndarray:
