@@ -239,9 +239,13 @@ int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, c
     }
 
     uint32_t* val_in = reinterpret_cast<uint32_t*>(binning + BL.val_in);
-    const int bit = (int)higher_msb(tiles);
+    // The reference sorts bits [0, 32 + getHigherMsb(tiles)) (rasterizer_impl.cu:306-311); tile ids are
+    // < tiles, so the bits of tiles - 1 are all the significant ones and a stable sort over just those
+    // gives the identical order.  This matters exactly at powers of two: the 4096^2 sun view has 65 536
+    // tiles = 16 significant bits (two 8-bit passes on 16-bit keys), where getHigherMsb says 17.
+    const int bit = tiles > 1 ? (int)higher_msb(tiles - 1) : 1;
 
-    // Tile ids fit 16 bits up to 65 535 tiles (4096^2 images): 16-bit sort keys cut the traffic of
+    // Tile ids fit 16 bits up to 65 536 tiles (4096^2 images): 16-bit sort keys cut the traffic of
     // every sort pass from 16 to 12 bytes per instance.  Larger grids sort 32-bit keys.
     auto run = [&](auto key_tag) -> int {
         using KeyT = decltype(key_tag);
@@ -275,7 +279,7 @@ int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, c
         EOGS_LAUNCH_CHECK("tile_ranges_kernel");
         return 0;
     };
-    if (int rc = tiles <= 0xFFFFu ? run(uint16_t{}) : run(uint32_t{})) return rc;
+    if (int rc = tiles <= 0x10000u ? run(uint16_t{}) : run(uint32_t{})) return rc;
     prof_mark(s, ST_RANGES);
     return 0;
 }
