@@ -87,6 +87,9 @@ SIGNATURES = {
     "eogs_prune_temp_bytes": (C.c_size_t, [C.c_int]),
     "eogs_prune_offsets": (C.c_int, [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "eogs_prune_gather": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_f32p, c_f32p]),
+    "eogs_densify_select": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_f32p, C.c_float, C.c_float, c_ptr, c_ptr]),
+    "eogs_densify_split_children": (C.c_int, [c_ptr, C.c_int, C.c_int, c_f32p, c_f32p, c_f32p, c_f32p]),
+    "eogs_densify_keep": (C.c_int, [c_ptr, C.c_int, C.c_int, c_ptr, c_f32p, c_f32p, C.c_float, C.c_float, c_ptr]),
     "eogs_knn_bytes": (C.c_size_t, [C.c_int]),
     "eogs_knn_dist2": (C.c_int, [c_ptr, C.c_int, c_f32p, c_ptr, C.c_size_t, c_f32p]),
     "eogs_dsm_splat": (C.c_int, [c_ptr, C.c_longlong, c_ptr, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,

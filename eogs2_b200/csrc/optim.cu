@@ -69,6 +69,79 @@ __global__ void prune_count_kernel(int P, const uint8_t* __restrict__ keep, cons
     *count = offsets[P - 1] + (keep[P - 1] ? 1u : 0u);
 }
 
+// ---- densification (densify_and_clone / densify_and_split / densify_and_prune, gaussian_model.py:573-704) ----
+// Selection masks on the P rows that existed before densification.  grads = xyz_gradient_accum / denom with
+// NaN -> 0 (:682-683); clone: |grads| >= thr and max(exp(log_scale)) <= percent_dense * extent (:633-640);
+// split: grads >= thr and max(exp(log_scale)) > percent_dense * extent (:581-586; rows appended by the clone
+// step have a padded gradient of 0 and are never selected).
+__global__ void __launch_bounds__(256)
+densify_select_kernel(int P, const float* __restrict__ grad_accum, const float* __restrict__ denom,
+                      const float* __restrict__ log_scales, float grad_threshold, float size_threshold,
+                      uint8_t* __restrict__ clone_flag, uint8_t* __restrict__ split_flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float g = grad_accum[i] / denom[i];
+    if (g != g) g = 0.f;
+    const float ms = fmaxf(fmaxf(expf(log_scales[3 * (size_t)i]), expf(log_scales[3 * (size_t)i + 1])),
+                           expf(log_scales[3 * (size_t)i + 2]));
+    clone_flag[i] = (fabsf(g) >= grad_threshold && ms <= size_threshold) ? 1 : 0;
+    split_flag[i] = (g >= grad_threshold && ms > size_threshold) ? 1 : 0;
+}
+
+// The K = N * Ks child rows of a split hold copies of their parents (gathered N times).  In place (:592-603):
+//   xyz += build_rotation(rotation) @ (noise * exp(log_scale));   log_scale = log(exp(log_scale) / (0.8 N))
+// build_rotation (utils/general_utils.py:82-105) normalises the quaternion.  noise [K,3] is standard normal,
+// drawn by the caller (torch.normal(0, stds) = randn * stds, :590-591) so that ranks share the stream.
+__global__ void __launch_bounds__(256)
+densify_split_children_kernel(int K, int N, float* __restrict__ xyz, float* __restrict__ log_scales,
+                              const float* __restrict__ rotations, const float* __restrict__ noise)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    float s[3], smp[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        s[k] = expf(log_scales[3 * (size_t)c + k]);
+        smp[k] = noise[3 * (size_t)c + k] * s[k];
+    }
+    const float q0 = rotations[4 * (size_t)c], q1 = rotations[4 * (size_t)c + 1], q2 = rotations[4 * (size_t)c + 2],
+                q3 = rotations[4 * (size_t)c + 3];
+    const float nrm = sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    const float r = q0 / nrm, x = q1 / nrm, y = q2 / nrm, z = q3 / nrm;
+    const float R[3][3] = {{1.f - 2.f * (y * y + z * z), 2.f * (x * y - r * z), 2.f * (x * z + r * y)},
+                           {2.f * (x * y + r * z), 1.f - 2.f * (x * x + z * z), 2.f * (y * z - r * x)},
+                           {2.f * (x * z - r * y), 2.f * (y * z + r * x), 1.f - 2.f * (x * x + y * y)}};
+    const float div = 0.8f * (float)N;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        xyz[3 * (size_t)c + k] += R[k][0] * smp[0] + R[k][1] * smp[1] + R[k][2] * smp[2];
+        log_scales[3 * (size_t)c + k] = logf(s[k] / div);
+    }
+}
+
+// Keep mask over the Pn rows after densification (:60x prune_filter of the split parents, then :690-700):
+// drop split parents, sigmoid(opacity) < min_opacity, and — when ws_threshold >= 0 — max(exp(log_scale)) >
+// ws_threshold (big_points_ws).  big_points_vs tests max_radii2D, which densification_postfix has just reset
+// to zeros (:571), so it never fires in the reference and is not evaluated here.
+__global__ void __launch_bounds__(256)
+densify_keep_kernel(int Pn, int P_old, const uint8_t* __restrict__ split_flag, const float* __restrict__ opacity_logits,
+                    const float* __restrict__ log_scales, float min_opacity, float ws_threshold,
+                    uint8_t* __restrict__ keep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Pn) return;
+    bool k = !(i < P_old && split_flag[i]);
+    const float op = 1.f / (1.f + expf(-opacity_logits[i]));
+    if (op < min_opacity) k = false;
+    if (ws_threshold >= 0.f) {
+        const float ms = fmaxf(fmaxf(expf(log_scales[3 * (size_t)i]), expf(log_scales[3 * (size_t)i + 1])),
+                               expf(log_scales[3 * (size_t)i + 2]));
+        if (ms > ws_threshold) k = false;
+    }
+    keep[i] = k ? 1 : 0;
+}
+
 }  // namespace eogs
 
 using namespace eogs;
@@ -135,6 +208,44 @@ EOGS_API int eogs_prune_gather(eogs_stream_t stream, int P, int width, const uin
     gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         P, width, keep, offsets, src, dst);
     EOGS_LAUNCH_CHECK("gather_rows_kernel");
+    return 0;
+}
+
+EOGS_API int eogs_densify_select(eogs_stream_t stream, int P, const float* grad_accum, const float* denom,
+                                 const float* log_scales, float grad_threshold, float size_threshold,
+                                 uint8_t* clone_flag, uint8_t* split_flag)
+{
+    if (P < 0) { set_error("bad P"); return -1; }
+    if (P == 0) return 0;
+    if (!grad_accum || !denom || !log_scales || !clone_flag || !split_flag) { set_error("null argument"); return -4; }
+    densify_select_kernel<<<(P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        P, grad_accum, denom, log_scales, grad_threshold, size_threshold, clone_flag, split_flag);
+    EOGS_LAUNCH_CHECK("densify_select_kernel");
+    return 0;
+}
+
+EOGS_API int eogs_densify_split_children(eogs_stream_t stream, int K, int N, float* xyz, float* log_scales,
+                                         const float* rotations, const float* noise)
+{
+    if (K < 0 || N <= 0) { set_error("bad sizes"); return -1; }
+    if (K == 0) return 0;
+    if (!xyz || !log_scales || !rotations || !noise) { set_error("null argument"); return -4; }
+    densify_split_children_kernel<<<(K + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        K, N, xyz, log_scales, rotations, noise);
+    EOGS_LAUNCH_CHECK("densify_split_children_kernel");
+    return 0;
+}
+
+EOGS_API int eogs_densify_keep(eogs_stream_t stream, int Pn, int P_old, const uint8_t* split_flag,
+                               const float* opacity_logits, const float* log_scales, float min_opacity,
+                               float ws_threshold, uint8_t* keep)
+{
+    if (Pn < 0 || P_old < 0 || P_old > Pn) { set_error("bad sizes"); return -1; }
+    if (Pn == 0) return 0;
+    if ((P_old > 0 && !split_flag) || !opacity_logits || !log_scales || !keep) { set_error("null argument"); return -4; }
+    densify_keep_kernel<<<(Pn + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        Pn, P_old, split_flag, opacity_logits, log_scales, min_opacity, ws_threshold, keep);
+    EOGS_LAUNCH_CHECK("densify_keep_kernel");
     return 0;
 }
 

@@ -129,3 +129,85 @@ class FlatGaussianAdam:
                                                           src.data_ptr() + 4 * a, dst.data_ptr() + 4 * na), "eogs_prune_gather")
         self._make_views()
         return self.params
+
+    # ---- densify --------------------------------------------------------------------------------
+    def _scan_flags(self, lib, stream, flags: torch.Tensor):
+        P = flags.numel()
+        offsets = torch.empty(max(P, 1), dtype=torch.int32, device=self.device)
+        tmp_bytes = lib.eogs_prune_temp_bytes(P)
+        tmp = torch.empty(tmp_bytes, dtype=torch.uint8, device=self.device)
+        count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        _cabi.check(lib.eogs_prune_offsets(stream, P, flags.data_ptr(), offsets.data_ptr(), tmp.data_ptr(), tmp_bytes,
+                                           count.data_ptr()), "eogs_prune_offsets")
+        return offsets, count
+
+    def densify_and_prune(self, xyz_gradient_accum: torch.Tensor, denom: torch.Tensor, grad_threshold: float,
+                          min_opacity: float, screen_size_threshold: float, max_screen_size, scene_extent: float,
+                          percent_dense: float = 0.01, N: int = 2,
+                          generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+        """GaussianModel.densify_and_prune (scene/gaussian_model.py:672-704) on the flat buffers: clone the small
+        Gaussians with a large view-space gradient, split the large ones into N samples of their own
+        distribution (parents removed), then prune by opacity (and, when max_screen_size is given, by world size
+        > 0.1 * screen_size_threshold).  Arguments follow the reference's order, with the two statistics tensors
+        in place of `self` state and without `radii` (only stored in tmp_radii there).
+        Row order is the reference's: [survivors | clones | split children, N blocks].  New rows get zero Adam
+        moments (cat_tensors_to_optimizer, :507-539).  The caller resets xyz_gradient_accum / denom /
+        max_radii2D to zeros of the new length like densification_postfix (:569-571).
+
+        `generator`: CUDA generator for the split samples; seed it identically on every rank (e.g. from the
+        iteration number) and the replicas stay bit-identical without a broadcast."""
+        for need in ("xyz", "opacity", "scaling", "rotation"):
+            if need not in self.slices:
+                raise ValueError(f"densify_and_prune needs the '{need}' segment")
+        lib, dev, P = _cabi.load(), self.device, self.P
+        if xyz_gradient_accum.numel() != P or denom.numel() != P:
+            raise ValueError("xyz_gradient_accum / denom must have one entry per Gaussian")
+        with torch.cuda.device(dev), torch.no_grad():
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            accum = xyz_gradient_accum.detach().to(torch.float32).reshape(-1).contiguous()
+            den = denom.detach().to(torch.float32).reshape(-1).contiguous()
+            clone_flag = torch.zeros(max(P, 1), dtype=torch.uint8, device=dev)
+            split_flag = torch.zeros(max(P, 1), dtype=torch.uint8, device=dev)
+            sa, _ = self.slices["scaling"]
+            _cabi.check(lib.eogs_densify_select(stream, P, accum.data_ptr(), den.data_ptr(), self.flat.data_ptr() + 4 * sa,
+                                                float(grad_threshold), float(percent_dense * scene_extent),
+                                                clone_flag.data_ptr(), split_flag.data_ptr()), "eogs_densify_select")
+            clone_off, clone_cnt = self._scan_flags(lib, stream, clone_flag[:P])
+            split_off, split_cnt = self._scan_flags(lib, stream, split_flag[:P])
+            Kc, Ks = (int(v) for v in torch.cat([clone_cnt, split_cnt]).tolist())      # one sync for both counts
+            Pn = P + Kc + N * Ks
+            noise = torch.randn((N * Ks, 3), device=dev, dtype=torch.float32, generator=generator)
+
+            old = (self.flat, self.exp_avg, self.exp_avg_sq, dict(self.slices))
+            self._alloc(Pn)                                   # zeros: new rows start with zero moments
+            for which, (src, dst) in enumerate(zip(old[:3], (self.flat, self.exp_avg, self.exp_avg_sq))):
+                for n in self.names:
+                    a, b = old[3][n]
+                    na, _ = self.slices[n]
+                    w = self.width[n]
+                    dst[na:na + P * w].copy_(src[a:b])
+                    if which != 0 or P == 0:
+                        continue
+                    if Kc:
+                        _cabi.check(lib.eogs_prune_gather(stream, P, w, clone_flag.data_ptr(), clone_off.data_ptr(),
+                                                          src.data_ptr() + 4 * a, dst.data_ptr() + 4 * (na + P * w)),
+                                    "eogs_prune_gather(clone)")
+                    for rep in range(N if Ks else 0):
+                        row0 = P + Kc + rep * Ks
+                        _cabi.check(lib.eogs_prune_gather(stream, P, w, split_flag.data_ptr(), split_off.data_ptr(),
+                                                          src.data_ptr() + 4 * a, dst.data_ptr() + 4 * (na + row0 * w)),
+                                    "eogs_prune_gather(split)")
+            if Ks:
+                row0 = P + Kc
+                ptr = lambda n, wdt: self.flat.data_ptr() + 4 * (self.slices[n][0] + row0 * wdt)   # noqa: E731
+                _cabi.check(lib.eogs_densify_split_children(stream, N * Ks, N, ptr("xyz", 3), ptr("scaling", 3),
+                                                            ptr("rotation", 4), noise.data_ptr()),
+                            "eogs_densify_split_children")
+            keep = torch.empty(max(Pn, 1), dtype=torch.uint8, device=dev)
+            ws = 0.1 * float(screen_size_threshold) if max_screen_size else -1.0
+            _cabi.check(lib.eogs_densify_keep(stream, Pn, P, split_flag.data_ptr(),
+                                              self.flat.data_ptr() + 4 * self.slices["opacity"][0],
+                                              self.flat.data_ptr() + 4 * self.slices["scaling"][0],
+                                              float(min_opacity), ws, keep.data_ptr()), "eogs_densify_keep")
+        self.last_densify = {"cloned": Kc, "split": Ks, "rows_before_prune": Pn}
+        return self.prune(keep[:Pn].bool())

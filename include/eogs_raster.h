@@ -284,6 +284,23 @@ EOGS_API int eogs_prune_offsets(eogs_stream_t stream, int P, const uint8_t* keep
 EOGS_API int eogs_prune_gather(eogs_stream_t stream, int P, int width, const uint8_t* keep,
                                const uint32_t* offsets, const float* src, float* dst);
 
+/* Densification (densify_and_prune = densify_and_clone + densify_and_split + prune, scene/gaussian_model.py:573-704)
+ * on the same flat layout; the row copies reuse eogs_prune_offsets / eogs_prune_gather.
+ *   eogs_densify_select: clone_flag / split_flag [P] u8 from grads = grad_accum / denom (NaN -> 0), grad_threshold and
+ *                        size_threshold = percent_dense * scene_extent (:581-586, :633-640)
+ *   eogs_densify_split_children: in place on the K = N*Ks child rows (copies of their parents):
+ *                        xyz += R(rotation) (noise * exp(log_scale)); log_scale = log(exp(log_scale) / (0.8 N)) (:590-603)
+ *   eogs_densify_keep:   keep [Pn] u8 after densification: not a split parent (rows < P_old), sigmoid(opacity) >=
+ *                        min_opacity, and max exp(log_scale) <= ws_threshold when ws_threshold >= 0 (:690-700) */
+EOGS_API int eogs_densify_select(eogs_stream_t stream, int P, const float* grad_accum, const float* denom,
+                                 const float* log_scales, float grad_threshold, float size_threshold,
+                                 uint8_t* clone_flag, uint8_t* split_flag);
+EOGS_API int eogs_densify_split_children(eogs_stream_t stream, int K, int N, float* xyz, float* log_scales,
+                                         const float* rotations, const float* noise);
+EOGS_API int eogs_densify_keep(eogs_stream_t stream, int Pn, int P_old, const uint8_t* split_flag,
+                               const float* opacity_logits, const float* log_scales, float min_opacity,
+                               float ws_threshold, uint8_t* keep);
+
 /* ---- simple-knn distCUDA2 ------------------------------------ */
 /* distCUDA2 (submodules/simple-knn/spatial.cu:15-26 -> SimpleKNN::knn, simple_knn.cu:187-222): for every point the
  * mean of the squared distances to its 3 nearest neighbours (other indices; duplicates count with distance 0;
