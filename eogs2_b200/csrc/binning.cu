@@ -26,6 +26,7 @@ GeomLayout geom_layout(int P) {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     L.splat = take(n * REC_F4 * sizeof(float4));
+    L.cut = take(n * 4);
     L.depth = take(n * 4);
     L.rect = take(n * 8);
     L.tiles = take(n * 4);

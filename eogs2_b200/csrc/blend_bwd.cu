@@ -44,6 +44,14 @@ constexpr int BWD_THREADS = BWD_WARPS * 32;
 constexpr int NPATCH = (TILE / PATCH_W) * (TILE / PATCH_H);   // 8
 constexpr int NSTRIP = NPATCH / 2;           // 4 strips of 16x4 pixels = a left and a right patch
 
+// Accuracy switches for A/B builds (tools/fuzz_check.py): accurate expf / IEEE division instead of
+// ex2.approx / rcp.approx for the VALUES (the accept decision never depends on them, see alpha_cut).
+#ifndef EOGS_BWD_EXACT_EXP
+#define EOGS_BWD_EXACT_EXP 0
+#endif
+#ifndef EOGS_BWD_EXACT_DIV
+#define EOGS_BWD_EXACT_DIV 0
+#endif
 // Tuning switches (A/B measured on B200): where the per-pixel dynamic state lives.
 #ifndef EOGS_BWD_STATE_SMEM
 #define EOGS_BWD_STATE_SMEM 0                // 1: T / accum in shared memory (-16 registers, +2 LDS/STS per strip)
@@ -54,6 +62,7 @@ constexpr int NSTRIP = NPATCH / 2;           // 4 strips of 16x4 pixels = a left
 struct BwdWarpSmem {
     float4 rec[2][32][REC_F4];        // two stages of 32 packed records (cp.async destinations, 48 B each)
     uint32_t rid[2][32];              // Gaussian id of each staged record
+    float cut[2][32];                 // alpha_cut of each staged record: accept iff power >= cut
     float4 pix[NSTRIP][4][32];        // [0] = {g0.L, g0.R, g1.L, g1.R}   [1] = {g2.L, g2.R, g3.L, g3.R}
                                       // [2] = {g4.L, g4.R, ginv.L, ginv.R}
                                       // [3] = {-T_final (bg . g).L, same .R, n_contrib.L, n_contrib.R (int bits)}
@@ -66,7 +75,8 @@ struct BwdWarpSmem {
 template <int C>
 __global__ void __launch_bounds__(BWD_THREADS, 4)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                 const float4* __restrict__ splat, const float* __restrict__ bg, int W, int H,
+                 const float4* __restrict__ splat, const float* __restrict__ alpha_cut,
+                 const float* __restrict__ bg, int W, int H,
                  int tiles_x, int tiles_y, int band_row0, int band_h,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, const float* __restrict__ dL_dinvdepth,
@@ -151,6 +161,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             const float4* src = splat + (size_t)id * REC_F4;
 #pragma unroll
             for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[0][lane][k], src + k);
+            cp_async4(&sm.cut[0][lane], alpha_cut + id);
         }
         cp_async_commit();
         if (p0 - 32 >= 0) id_next = __ldg(list + p0 - 32);
@@ -180,6 +191,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             const float4* src = splat + (size_t)id_next * REC_F4;
 #pragma unroll
             for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[stage ^ 1][lane][k], src + k);
+            cp_async4(&sm.cut[stage ^ 1][lane], alpha_cut + id_next);
         }
         cp_async_commit();
         if (pos - 64 >= 0) id_next = __ldg(list + pos - 64);
@@ -193,6 +205,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             const float4 rb = sm.rec[stage][e][1];     // conic.z, opacity, c0, c1
             const float4 rc = sm.rec[stage][e][2];     // c2, c3, c4, 1/depth
             const float col[5] = {rb.z, rb.w, rc.x, rc.y, rc.z};
+            const float cut_e = sm.cut[stage][e];      // the forward accepted a pixel of this entry iff power >= cut_e
 
             f2 v2[NV];
 #pragma unroll
@@ -219,14 +232,22 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 const float cyy = __fmul_rn(__fmul_rn(rb.x, dy), dy);
                 const f2 quad2 = fma2(dx2, zdx2, bc2(cyy));
                 const f2 power2 = fma2(quad2, bc2(-0.5f), mul2(wdx2, bc2(-dy)));
-                // exp through ex2.approx: gradients carry a 1e-3 bar, not the forward's bit-exact one
+                // exp through ex2.approx (relative error ~2^-22): the VALUES carry a 1e-3 bar.  The accept
+                // DECISION alpha >= 1/255 must be the forward's, or a pixel on that contour flips and a whole
+                // term appears / disappears (1e-3..1e-2 in small scenes, tools/fuzz_parity.py).  It is taken on
+                // the exponent instead: power >= alpha_cut, the per-Gaussian threshold the preprocess derived
+                // from the forward's own expf (geom_math.cuh: alpha_cut_of) — same decision, same instruction count.
+#if EOGS_BWD_EXACT_EXP
+                const float G0 = expf(lo2(power2)), G1 = expf(hi2(power2));
+#else
                 const f2 pl2 = mul2(power2, bc2(1.4426950408889634f));
                 const float G0 = ex2_approx(lo2(pl2)), G1 = ex2_approx(hi2(pl2));
+#endif
                 const f2 og2 = mul2(bc2(rb.y), mk2(G0, G1));
                 const float al0 = fminf(0.99f, lo2(og2)), al1 = fminf(0.99f, hi2(og2));
                 // entry at list position pos_e is blended by a pixel iff pos_e < n_contrib (backward.cu:556-558)
-                const bool v0 = pos_e < ncon[2 * r] && !(lo2(power2) > 0.0f) && !(al0 < 1.0f / 255.0f);
-                const bool v1 = pos_e < ncon[2 * r + 1] && !(hi2(power2) > 0.0f) && !(al1 < 1.0f / 255.0f);
+                const bool v0 = pos_e < ncon[2 * r] && !(lo2(power2) > 0.0f) && !(lo2(power2) < cut_e);
+                const bool v1 = pos_e < ncon[2 * r + 1] && !(hi2(power2) > 0.0f) && !(hi2(power2) < cut_e);
                 a2[r] = mk2(v0 ? al0 : 0.f, v1 ? al1 : 0.f);
                 Gv2[r] = mk2(v0 ? G0 : 0.f, v1 ? G1 : 0.f);
                 if (__any_sync(FULL, v0 || v1)) live |= 1u << r;
@@ -253,7 +274,11 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 const f2 Told2 = T2[r], accum_old2 = accum2[r];
 #endif
                 const f2 om2 = fma2(a2[r], bc2(-1.f), bc2(1.f));                // 1 - alpha
+#if EOGS_BWD_EXACT_DIV
+                const f2 inv2 = mk2(__fdiv_rn(1.f, lo2(om2)), __fdiv_rn(1.f, hi2(om2)));
+#else
                 const f2 inv2 = mk2(fast_rcp(lo2(om2)), fast_rcp(hi2(om2)));    // exactly 1 for a rejected pixel
+#endif
                 const f2 Tn2 = mul2(Told2, inv2);
                 const f2 w2 = mul2(a2[r], Tn2);
                 f2 cg2 = mul2(bc2(rc.w), ginv2);
@@ -308,7 +333,8 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
         if (attr_err != cudaSuccess) return;
         kernel<<<grid, BWD_THREADS, smem, s>>>(
             reinterpret_cast<const uint2*>(image + IL.ranges), point_list,
-            reinterpret_cast<const float4*>(geom + GL.splat), bg, W, H, tiles_x, tiles_y,
+            reinterpret_cast<const float4*>(geom + GL.splat), reinterpret_cast<const float*>(geom + GL.cut),
+            bg, W, H, tiles_x, tiles_y,
             band.row_begin, band.height(H), reinterpret_cast<const float*>(image + IL.final_T),
             reinterpret_cast<const uint32_t*>(image + IL.n_contrib), dL_dpix, dL_dinvdepth, grad_rec);
     };

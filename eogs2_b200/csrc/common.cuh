@@ -25,6 +25,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 struct GeomLayout {
     size_t splat;        // float4[3P]
+    size_t cut;          // float[P]     alpha_cut: the forward accepts a pixel iff power >= cut (blend backward)
     size_t depth;        // float[P]     200 - altitude (garbage-free: culled entries hold +inf bits)
     size_t rect;         // uint2[P]     (x0 | y0<<16, x1 | y1<<16) tile rect, exclusive max
     size_t tiles;        // u32[P]       tiles touched
@@ -182,6 +183,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif

@@ -41,7 +41,7 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
                       const float* __restrict__ view, const float* __restrict__ alt_affine,
                       float scale_modifier, bool antialiasing,
                       int align_mask, int32_t* __restrict__ radii, float4* __restrict__ splat,
-                      float* __restrict__ depth, uint2* __restrict__ rect,
+                      float* __restrict__ alpha_cut, float* __restrict__ depth, uint2* __restrict__ rect,
                       uint32_t* __restrict__ tiles, uint32_t* __restrict__ key_in,
                       uint32_t* __restrict__ id_in, eogs_forward_info* __restrict__ info)
 {
@@ -166,6 +166,7 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
     id_in[idx] = (uint32_t)idx;
     float4* rec = splat + (size_t)idx * REC_F4;
     rec[0] = r0; rec[1] = r1; rec[2] = r2;
+    alpha_cut[idx] = out_radius > 0 ? alpha_cut_of(r1.y) : __int_as_float(0x7f800000);
 }
 
 int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int channels, bool raw_params,
@@ -183,7 +184,8 @@ int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int ch
         kernel<<<blocks, PRE_THREADS, 0, s>>>(
             P, W, H, grid_x, grid_y, band.row_begin, band.row_end, means3D, scales, reinterpret_cast<const float4*>(rotations),
             cov3D_precomp, opacities, colors, view, alt_affine, scale_modifier, antialiasing, align_mask, radii,
-            reinterpret_cast<float4*>(geom + L.splat), reinterpret_cast<float*>(geom + L.depth),
+            reinterpret_cast<float4*>(geom + L.splat), reinterpret_cast<float*>(geom + L.cut),
+            reinterpret_cast<float*>(geom + L.depth),
             reinterpret_cast<uint2*>(geom + L.rect), reinterpret_cast<uint32_t*>(geom + L.tiles),
             reinterpret_cast<uint32_t*>(geom + L.key_in), reinterpret_cast<uint32_t*>(geom + L.order),
             info_dev);

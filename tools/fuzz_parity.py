@@ -1,0 +1,85 @@
+"""Randomised parity sweep against the COMPILED REFERENCE (oracle/_ref) on the GPU box: many small random
+configurations (ragged sizes down to 1x1, P down to 1, both scene kinds, antialiasing, scale_modifier, sun view),
+bit-exact on every integer / key / image bit, 1e-3 relative on gradients.  Development tool (not collected by
+pytest):   python tools/fuzz_parity.py --cases 80 --seed 0 > gpurun_out/<tag>/fuzz.json"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
+import test_parity_gpu as T                       # noqa: E402
+from oracle import ref_rasterizer as R            # noqa: E402
+import eogs2_b200 as E                            # noqa: E402
+
+
+def one(dev, rng, idx):
+    P = int(rng.choice([1, 2, 7, 33, 500, 4000, 20000, 60000]))
+    W, H = int(rng.integers(1, 900)), int(rng.integers(1, 900))
+    if rng.random() < 0.2:
+        W, H = int(rng.choice([1, 15, 16, 17, 256])), int(rng.choice([1, 15, 16, 17, 256]))
+    kind = "trained" if rng.random() < 0.7 else "init"
+    aa, sun = bool(rng.random() < 0.3), bool(rng.random() < 0.2)
+    mod = float(rng.choice([1.0, 1.0, 0.6, 1.4]))
+    seed = int(rng.integers(0, 10_000))
+    c = T.make_case(P, W, H, kind, seed, aa, mod, sun)
+    W, H = c["W"], c["H"]
+    st, ex, g = T.run_mine(dev, c)
+    d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in c.items()}
+    empty, campos = torch.empty(0, device=dev), torch.zeros(3, device=dev)
+    rs = R.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], mod, empty,
+                   d["view"], d["view"], 1.0, 1.0, H, W, campos, False, aa)
+    rx = R.export_state(rs)
+    gr = R.backward(rs, d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], mod, empty,
+                    d["view"], d["view"], 1.0, 1.0, d["dL_dcolor"], d["dL_dinvdepth"], campos, aa)
+    torch.cuda.synchronize()
+    bad = []
+    if st.num_rendered != rs.num_rendered:
+        bad.append("num_rendered")
+    for k in ("radii", "tiles_touched", "point_list", "keys_sorted", "ranges", "n_contrib"):
+        if not torch.equal(ex[k].long(), rx[k].long()):
+            bad.append(k)
+    for a, b, k in ((st.color, rs.color, "color"), (st.invdepth, rs.invdepth, "invdepth"), (ex["final_T"], rx["final_T"], "final_T")):
+        if not torch.equal(a.view(torch.int32), b.view(torch.int32)):
+            bad.append(k)
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", None, "dL_dscales", "dL_drotations"]
+    worst = 0.0
+    for nm, t in zip(names, g):
+        if nm is None or (nm == "dL_drotations" and kind == "init"):
+            continue
+        ref = gr[nm].cpu().numpy()
+        if np.abs(ref).max() < 1e-12:
+            continue
+        r = T.rel(t.cpu().numpy(), ref)
+        worst = max(worst, r)
+        if r >= T.GRAD_RTOL:
+            bad.append(f"{nm}:{r:.2e}")
+    return dict(case=idx, P=P, W=W, H=H, kind=kind, aa=aa, sun=sun, mod=mod, seed=seed, I=int(st.num_rendered),
+                worst_grad_rel=worst, bad=bad)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=60)
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(a.seed)
+    rows = []
+    for i in range(a.cases):
+        row = one(dev, rng, i)
+        rows.append(row)
+        if row["bad"]:
+            print("MISMATCH", row, file=sys.stderr)
+    nbad = sum(1 for r in rows if r["bad"])
+    print(json.dumps({"cases": len(rows), "mismatching_cases": nbad,
+                      "worst_grad_rel": max(r["worst_grad_rel"] for r in rows), "rows": rows}, indent=1))
+    print(f"fuzz: {len(rows)} cases, {nbad} with mismatches", file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()
