@@ -86,11 +86,6 @@ struct GatherTiles {
     __host__ __device__ uint32_t operator()(uint32_t g) const { return tiles[g]; }
 };
 
-__global__ void publish_info_kernel(const uint32_t* __restrict__ offsets, int P,
-                                    eogs_forward_info* __restrict__ info) {
-    info->num_instances = offsets[P - 1];
-}
-
 int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
                        eogs_forward_info* info_dev)
 {
@@ -123,8 +118,7 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
     need = L.temp_bytes;
     EOGS_CUDA(cub::DeviceScan::InclusiveSum(temp, need, in, offsets, P, s));
 
-    publish_info_kernel<<<1, 1, 0, s>>>(offsets, P, info_dev);
-    EOGS_LAUNCH_CHECK("publish_info_kernel");
+    (void)info_dev;      // num_instances = offsets[P-1] was already published by the preprocess kernel
     prof_mark(s, ST_SCAN);
     return 0;
 }

@@ -153,10 +153,17 @@ static int forward_geometry_impl(eogs_stream_t stream, int P, int W, int H, int 
                                            cov3D_precomp, opacities, colors, viewmatrix, alt_affine, scale_modifier,
                                            antialiasing != 0, radii, g, L, info_dev)) return rc;
         prof_mark(s, ST_PREPROCESS);
-        if (int rc = launch_depth_order(s, P, g, L, info_dev)) return rc;
     }
+    // The preprocess kernel has published I and the error word: hand them to the host NOW, with the `ready` word
+    // set, and only then enqueue the depth sort and the scan.  A host that polls info_host->ready (pinned memory)
+    // gets I while those still run and can enqueue the render stage behind them: the GPU never waits for the host
+    // round trip (the reference blocks on a cudaMemcpy after its scan, rasterizer_impl.cu:284).
+    EOGS_CUDA(cudaMemsetAsync(&info_dev->ready, 0x01, sizeof(uint32_t), s));
     if (info_host)
         EOGS_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(eogs_forward_info), cudaMemcpyDeviceToHost, s));
+    if (P > 0) {
+        if (int rc = launch_depth_order(s, P, static_cast<char*>(geom), geom_layout(P), info_dev)) return rc;
+    }
     return 0;
 }
 

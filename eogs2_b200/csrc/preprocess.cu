@@ -164,6 +164,14 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
     depth[idx] = out_depth;
     key_in[idx] = out_key;
     id_in[idx] = (uint32_t)idx;
+    // I = sum of tiles touched is published here, by one red.global per warp, instead of after the depth sort and
+    // scan: the host needs it to size the binning buffers, and its device -> host copy can then overlap those
+    // two library calls (cabi.cu: forward_geometry_impl).  u32 wrap-around like the reference's scan.
+    {
+        const uint32_t active = __activemask();
+        const uint32_t wsum = __reduce_add_sync(active, out_tiles);
+        if (lane_id() == (uint32_t)(__ffs(active) - 1) && wsum) atomicAdd(&info->num_instances, wsum);
+    }
     float4* rec = splat + (size_t)idx * REC_F4;
     rec[0] = r0; rec[1] = r1; rec[2] = r2;
     alpha_cut[idx] = out_radius > 0 ? alpha_cut_of(r1.y) : __int_as_float(0x7f800000);

@@ -27,7 +27,7 @@ import torch
 
 from . import _cabi
 from .rasterizer import (ERR_ALTITUDE_ABOVE_200, ForwardState, GaussianRasterizationSettings, GaussianRasterizer,
-                         _debug_sync, _f32c, _info_host, _ptr, assemble_grad_viewmatrix)
+                         _debug_sync, _f32c, _info_host, _ptr, _wait_info, assemble_grad_viewmatrix)
 
 SH_C0 = 0.28209479177387814        # utils/sh_utils.py:25
 
@@ -71,9 +71,8 @@ def forward_params_raw(bg, xyz, features_dc, opacity_logits, log_scales, raw_rot
             stream, P, W, H, rb, re, _ptr(xyz), _ptr(log_scales), _ptr(raw_rotations), _ptr(opacity_logits),
             _ptr(features_dc), _ptr(alt_affine), _ptr(viewmatrix), float(scale_modifier), int(bool(antialiasing)),
             radii.data_ptr(), geom.data_ptr(), info_dev, info_host.data_ptr()), "eogs_forward_geometry_params_band")
-        torch.cuda.current_stream(dev).synchronize()
-        num_rendered = int(info_np[0]) & 0xFFFFFFFF
-        if int(info_np[1]) & ERR_ALTITUDE_ABOVE_200:
+        num_rendered, err = _wait_info(info_np, dev)
+        if err & ERR_ALTITUDE_ABOVE_200:
             raise RuntimeError("Point is too high: a Gaussian's altitude exceeds 200 (depth = 200 - altitude < 0)")
         _debug_sync(debug, "preprocess")
         image = torch.empty(lib.eogs_image_bytes_band(W, H, rb, re), dtype=torch.uint8, device=dev)

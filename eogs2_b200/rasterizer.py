@@ -81,10 +81,27 @@ def _info_host(device: torch.device) -> torch.Tensor:
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     t = _pinned_info.get(key)
     if t is None:
-        t = torch.zeros(2, dtype=torch.int32).pin_memory()
+        t = torch.zeros(4, dtype=torch.int32).pin_memory()          # eogs_forward_info: I, error, ready, reserved
         t = (t, t.numpy())                 # the numpy view reads the pinned words without a torch dispatch
         _pinned_info[key] = t
+    t[1][2] = 0                            # `ready` is raised by the device -> host copy of this call
     return t
+
+
+def _wait_info(info_np, device: torch.device):
+    """Wait for the geometry stage's (I, error) words.  Their copy into pinned memory is enqueued right after the
+    projection kernel, before the depth sort and the scan, so polling the `ready` word returns while those still
+    run and the render stage can be enqueued behind them without a GPU bubble (the reference blocks on a
+    cudaMemcpy after its scan, rasterizer_impl.cu:284).  Bounded: after a few hundred microseconds of polling it
+    falls back to a stream synchronisation, which also surfaces CUDA errors."""
+    for _ in range(4000):
+        if info_np[2] != 0:
+            break
+    else:
+        torch.cuda.current_stream(device).synchronize()
+        if info_np[2] == 0:
+            raise _cabi.EogsRasterError("geometry stage finished without publishing its instance count")
+    return int(info_np[0]) & 0xFFFFFFFF, int(info_np[1])
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -174,9 +191,7 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
             radii.data_ptr(), geom.data_ptr(), info_dev, info_host.data_ptr()), "eogs_forward_geometry_band")
         # The instance count sizes the binning buffers (reference: blocking cudaMemcpy,
         # rasterizer_impl.cu:284).
-        torch.cuda.current_stream(dev).synchronize()
-        num_rendered = int(info_np[0]) & 0xFFFFFFFF
-        err = int(info_np[1])
+        num_rendered, err = _wait_info(info_np, dev)
         if err & ERR_ALTITUDE_ABOVE_200:
             # reference: device printf("Point is too high") + __trap() (forward.cu:267-272)
             raise RuntimeError("Point is too high: a Gaussian's altitude exceeds 200 (depth = 200 - altitude < 0)")

@@ -51,7 +51,7 @@ extern "C" {
 #define EOGS_API
 #endif
 
-#define EOGS_ABI_VERSION 4
+#define EOGS_ABI_VERSION 5
 #define EOGS_TILE 16            /* BLOCK_X = BLOCK_Y = 16, DGR/cuda_rasterizer/config.h:15-16 */
 #define EOGS_MAX_CHANNELS 5     /* NUM_CHANNELS 5,        DGR/cuda_rasterizer/config.h:14    */
 
@@ -60,10 +60,15 @@ extern "C" {
 
 typedef void* eogs_stream_t;    /* cudaStream_t */
 
-/* Host-visible result of the geometry stage (write target must be pinned host memory). */
+/* Host-visible result of the geometry stage (write target must be pinned host memory).  The copy to
+ * info_host is enqueued right after the projection kernel, BEFORE the depth sort and the scan: a host that
+ * zeroes info_host->ready before the call and polls it afterwards has I while the rest of the geometry stage
+ * still runs; a host that synchronises the stream sees the same values. */
 typedef struct eogs_forward_info {
     uint32_t num_instances;     /* I = sum of tiles touched = reference's num_rendered */
     uint32_t error;             /* EOGS_ERR_* bits */
+    uint32_t ready;             /* non-zero once num_instances / error are final */
+    uint32_t reserved;
 } eogs_forward_info;
 
 EOGS_API int eogs_abi_version(void);

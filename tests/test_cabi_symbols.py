@@ -44,7 +44,7 @@ def test_only_the_c_abi_is_exported():
 def test_size_queries_are_host_only_and_monotonic():
     from eogs2_b200 import _cabi
     lib = _cabi.load()
-    assert lib.eogs_abi_version() == 4
+    assert lib.eogs_abi_version() == 5
     g1, g2 = lib.eogs_geom_bytes(1000), lib.eogs_geom_bytes(1_000_000)
     assert 0 < g1 < g2 and g2 >= 1_000_000 * (48 + 4 + 8 + 4 * 6)
     assert lib.eogs_image_bytes(2048, 2048) >= 2048 * 2048 * 8 + 16384 * 8
