@@ -465,25 +465,25 @@ def main():
 
     value = world * args.steps / (total_ms / 1e3)
     # roofline of the dominant kernel: blend backward.  Algorithmic bytes per launch:
-    # per instance 4 B id + 48 B record gathered + 44 B (11 floats) reduced into the gradient record;
+    # per instance 4 B id + 48 B record + 4 B alpha_cut gathered + 44 B (11 floats) reduced into the gradient record;
     # per pixel 4*(C+1) B upstream gradient + 8 B final_T / n_contrib.
-    bwd_bytes = I * (4 + 48 + 44) + IMG * IMG * (4 * 6 + 8)
+    bwd_bytes = I * (4 + 48 + 4 + 44) + IMG * IMG * (4 * 6 + 8)
     bwd_ms = stage_ms[STAGES.index("blend_bwd")]
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
     # DRAM traffic of one launch from the committed `ncu --set full` capture of this same command
-    # (profiles/r01o_blend_full.txt: dram__bytes_read.sum 257.96 MB + dram__bytes_write.sum 23.11 MB).  It is far
+    # (profiles/r03n_blend_full.txt: dram__bytes_read.sum 263.80 MB + dram__bytes_write.sum 22.54 MB).  It is far
     # BELOW the algorithmic bytes: records are gathered from L2 (126 MB holds the 48 MB record array) and list
     # entries behind the tile's last contributor are never fetched — the kernel is not HBM-bound.
-    NCU_BWD_TRAFFIC = 257_955_584 + 23_106_816
+    NCU_BWD_TRAFFIC = 263_799_808 + 22_537_984
     line = dict(base, value=value, ms_per_step=total_ms / args.steps, clocks=clocks,
                 e2e=None if e2e_ms is None else {"value": world * args.steps / (e2e_ms / 1e3), "unit": "renders/s",
                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                gpu_launches=7 * args.steps,
+                gpu_launches=6 * args.steps,   # preprocess, emit, tile ranges, blend fwd, blend bwd, preprocess bwd (CUB sorts/scans not counted)
                 roofline={"kernel": "blend_bwd_kernel<5>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                           "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_BWD_TRAFFIC, "peak_source": peak_src,
                           "ms_per_launch": bwd_ms, "algorithmic_bytes": bwd_bytes,
-                          "traffic_source": "profiles/r01o_blend_full.txt (ncu --set full, same workload)",
-                          "issue_active_pct_ncu": 63.9,
+                          "traffic_source": "profiles/r03n_blend_full.txt (ncu --set full, same workload)",
+                          "issue_active_pct_ncu": 63.8,
                           "note": "issue-bound, not HBM-bound: ncu smsp__issue_active 64 % with 16 resident warps/SM "
                                   "(register + shared-memory limited), DRAM throughput 2 % of peak; the HBM fraction is "
                                   "reported because the contract asks for it, the binding ceiling is the issue rate "
