@@ -97,10 +97,11 @@ def render_sharded(render_band: Callable[[Tuple[int, int]], Tuple[torch.Tensor, 
     invdepth[1,h,W])` and (optionally) all-gather the full images.  Returns
     (color, invdepth, band): full images when gather=True, else this rank's bands."""
     grid_y = (H + TILE - 1) // TILE
+    if grid_y < world:
+        # raised on EVERY rank (a rank that bailed out alone would leave the others in the all-gather)
+        raise RuntimeError(f"{grid_y} tile rows cannot be sharded over {world} ranks: use at most {grid_y}")
     bands = split_rows(grid_y, world, weights)
     band = bands[rank]
-    if band[0] == band[1]:
-        raise RuntimeError(f"rank {rank} has no tile rows: {grid_y} rows over {world} ranks")
     color, invdepth = render_band(band)
     if gather and world > 1:
         both = gather_bands(torch.cat([color, invdepth], 0), bands, H, group)

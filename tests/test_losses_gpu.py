@@ -40,7 +40,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("C,H,W,lam,seed", [(3, 128, 160, 0.2, 1), (1, 67, 45, 0.2, 2), (3, 16, 16, 1.0, 3),
-                                            (5, 40, 300, 0.0, 4), (3, 512, 512, 0.2, 5)])
+                                            (5, 40, 300, 0.0, 4), (3, 512, 512, 0.2, 5), (1, 166, 113, 1.0, 7492)])
 def test_photometric_loss_matches_torch(cuda_dev, C, H, W, lam, seed):
     g = torch.Generator().manual_seed(seed)
     gt = torch.rand(C, H, W, generator=g).to(cuda_dev)
@@ -49,13 +49,18 @@ def test_photometric_loss_matches_torch(cuda_dev, C, H, W, lam, seed):
     a = base.clone().requires_grad_(True)
     b = base.clone().requires_grad_(True)
     up = 1.7
-    loss_ref = ref_photometric(a, gt, lam)
-    (loss_ref * up).backward()
+    # fp32 reference: with one channel the reference's conv2d is an ordinary (non-depthwise) convolution, for which
+    # cuDNN may pick TF32 tensor-core algorithms (torch.backends.cudnn.allow_tf32 defaults to True) — 3e-4 relative
+    # noise in ITS gradient (found by tools/fuzz_misc.py).  The kernel under test is fp32 throughout.
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        loss_ref = ref_photometric(a, gt, lam)
+        (loss_ref * up).backward()
     loss, ssim_mean, l1_mean = L.photometric_loss(b, gt, lam, return_parts=True)
     (loss * up).backward()
     assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-5 * max(1.0, abs(float(loss_ref.detach())))
     assert abs(float(l1_mean) - float(torch.abs(base - gt).mean())) <= 1e-6
-    assert abs(float(ssim_mean) - float(ref_ssim(base, gt))) <= 1e-5
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        assert abs(float(ssim_mean) - float(ref_ssim(base, gt))) <= 1e-5
     assert b.grad.shape == a.grad.shape and rel(b.grad, a.grad) < 1e-4, rel(b.grad, a.grad)
 
 
