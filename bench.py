@@ -347,6 +347,10 @@ def main():
         world = 1
     if world > 1:
         import torch.distributed as dist
+        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at the VERSION
+        # level some images export) out of it; an explicit NCCL_DEBUG=INFO / TRACE from the caller is respected
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     wl = make_workload(dev, rank)
