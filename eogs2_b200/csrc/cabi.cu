@@ -207,6 +207,13 @@ EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, in
                                       radii, geom, info_dev, info_host);
 }
 
+EOGS_API int eogs_debug_alpha_cut(eogs_stream_t stream, int n, const float* opacity, float* cut, uint32_t* flags)
+{
+    if (n < 0) { set_error("bad n"); return -1; }
+    if (n > 0 && (!opacity || !cut || !flags)) { set_error("null argument"); return -4; }
+    return launch_alpha_cut_debug(static_cast<cudaStream_t>(stream), n, opacity, cut, flags);
+}
+
 EOGS_API int eogs_forward_render_band(eogs_stream_t stream, int P, int W, int H, int channels,
                         int row_begin, int row_end,
                         uint32_t num_instances, const void* geom, uint32_t* point_list,

@@ -107,6 +107,8 @@ int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int ch
                           const float* view, const float* alt_affine, float scale_modifier, bool antialiasing,
                           int32_t* radii, char* geom, const GeomLayout& L, eogs_forward_info* info_dev);
 
+int launch_alpha_cut_debug(cudaStream_t s, int n, const float* op, float* cut, uint32_t* flags);
+
 int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
                        eogs_forward_info* info_dev);
 

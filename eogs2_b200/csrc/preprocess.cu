@@ -177,6 +177,31 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
     alpha_cut[idx] = out_radius > 0 ? alpha_cut_of(r1.y) : __int_as_float(0x7f800000);
 }
 
+// Inspection (tests): alpha_cut_of on an array of opacities, plus the two facts that define it —
+// flags bit 0: the forward's test accepts power = cut; bit 1: it still accepts the next float below cut.
+__global__ void alpha_cut_debug_kernel(int n, const float* __restrict__ op, float* __restrict__ cut,
+                                       uint32_t* __restrict__ flags)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float o = op[i], c = alpha_cut_of(o);
+    cut[i] = c;
+    uint32_t f = 0u;
+    if (c <= 0.f && c > -3.0e38f) {
+        const uint32_t k = __float_as_uint(c) | 0x80000000u;
+        if (!(__fmul_rn(o, expf_as_forward(__uint_as_float(k))) < 1.0f / 255.0f)) f |= 1u;
+        if (!(__fmul_rn(o, expf_as_forward(__uint_as_float(k + 1u))) < 1.0f / 255.0f)) f |= 2u;
+    }
+    flags[i] = f;
+}
+
+int launch_alpha_cut_debug(cudaStream_t s, int n, const float* op, float* cut, uint32_t* flags) {
+    if (n <= 0) return 0;
+    alpha_cut_debug_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, op, cut, flags);
+    EOGS_LAUNCH_CHECK("alpha_cut_debug_kernel");
+    return 0;
+}
+
 int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int channels, bool raw_params,
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities, const float* colors,

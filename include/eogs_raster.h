@@ -355,6 +355,12 @@ EOGS_API int eogs_export_state(eogs_stream_t stream, int P, int W, int H, uint32
                       uint32_t* tiles_touched, uint64_t* keys_sorted,
                       uint32_t* ranges, float* final_T, uint32_t* n_contrib);
 
+/* alpha_cut of an array of (antialias-scaled) opacities: the smallest exponent `power` for which the forward's
+ * test !(opacity * expf(power) < 1/255) (forward.cu:367-372) accepts a pair; +inf when it never does.  The blend
+ * backward takes its accept decision from this per-Gaussian threshold.  flags bit 0: the test accepts power = cut,
+ * bit 1: it still accepts the next float below cut (must be 0). */
+EOGS_API int eogs_debug_alpha_cut(eogs_stream_t stream, int n, const float* opacity, float* cut, uint32_t* flags);
+
 /* Band variant: tiles_touched counts the band's tiles, keys_sorted carry whole-image tile ids,
  * ranges [band tiles,2], final_T / n_contrib [band_h*W]. */
 EOGS_API int eogs_export_state_band(eogs_stream_t stream, int P, int W, int H, int row_begin, int row_end,
