@@ -39,7 +39,12 @@
 
 namespace eogs {
 
-constexpr int BWD_WARPS = 4;                 // tiles per CTA: a 2x2 block of tiles
+#ifndef EOGS_BWD_WARPS
+#define EOGS_BWD_WARPS 4                     // tiles (= warps) per CTA: 4 = a 2x2 block of tiles, 2 = 2x1, 1 = one tile
+#endif
+constexpr int BWD_WARPS = EOGS_BWD_WARPS;
+constexpr int BWD_WX = BWD_WARPS >= 2 ? 2 : 1, BWD_WY = BWD_WARPS >= 4 ? 2 : 1;
+static_assert(BWD_WX * BWD_WY == BWD_WARPS, "EOGS_BWD_WARPS must be 1, 2 or 4");
 constexpr int BWD_THREADS = BWD_WARPS * 32;
 constexpr int NPATCH = (TILE / PATCH_W) * (TILE / PATCH_H);   // 8
 constexpr int NSTRIP = NPATCH / 2;           // 4 strips of 16x4 pixels = a left and a right patch
@@ -73,7 +78,7 @@ struct BwdWarpSmem {
 
 // 4 CTAs (16 warps) per SM measured best: 3 (142 regs) and 5 (96 regs) are both 14 % slower.
 template <int C>
-__global__ void __launch_bounds__(BWD_THREADS, 4)
+__global__ void __launch_bounds__(BWD_THREADS, 16 / BWD_WARPS)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ splat, const float* __restrict__ alpha_cut,
                  const float* __restrict__ bg, int W, int H,
@@ -89,7 +94,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     // tiles_y = tile rows of the band; brow = row inside the band, tile_y = row in the image
-    const int tile_x = (int)blockIdx.x * 2 + (int)(warp & 1u), brow = (int)blockIdx.y * 2 + (int)(warp >> 1);
+    const int tile_x = (int)blockIdx.x * BWD_WX + (int)(warp % BWD_WX), brow = (int)blockIdx.y * BWD_WY + (int)(warp / BWD_WX);
     if (tile_x >= tiles_x || brow >= tiles_y) return;            // whole warp leaves; no block barriers below
     const int tile_y = brow + band_row0;
     BwdWarpSmem& sm = s_warp[warp];
@@ -325,7 +330,7 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
                      const float* dL_dinvdepth, float* grad_rec)
 {
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = band.rows();
-    const dim3 grid((tiles_x + 1) / 2, (tiles_y + 1) / 2, 1);
+    const dim3 grid((tiles_x + BWD_WX - 1) / BWD_WX, (tiles_y + BWD_WY - 1) / BWD_WY, 1);
     constexpr size_t smem = sizeof(BwdWarpSmem) * BWD_WARPS;
     cudaError_t attr_err = cudaSuccess;
     auto run = [&](auto kernel) {
