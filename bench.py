@@ -347,10 +347,9 @@ def main():
         world = 1
     if world > 1:
         import torch.distributed as dist
-        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at the VERSION
-        # level some images export) out of it; an explicit NCCL_DEBUG=INFO / TRACE from the caller is respected
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries ONE JSON line: NCCL writes its debug output — including the "NCCL version ..." banner it
+        # prints at the VERSION and WARN levels — to stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     wl = make_workload(dev, rank)
