@@ -324,6 +324,18 @@ def cpu_baseline(wl, seconds_hint=20.0):
 
 
 # ----------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(text: str) -> None:
+    """The result line goes to the process's original stdout (see the fd juggling around the NCCL init)."""
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, (text + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,9 +359,13 @@ def main():
         world = 1
     if world > 1:
         import torch.distributed as dist
-        # stdout carries ONE JSON line: NCCL writes its debug output — including the "NCCL version ..." banner it
-        # prints at the VERSION and WARN levels — to stdout unless told otherwise
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries ONE JSON line, but NCCL writes its debug output — including the "NCCL version ..." banner of
+        # the VERSION / WARN levels this image exports — straight to file descriptor 1.  Point fd 1 at stderr for the
+        # rest of the run and keep the real stdout for the result line (emit()).
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     wl = make_workload(dev, rank)
@@ -398,7 +414,7 @@ def main():
                                             "kernels (DGR cuda_rasterizer, compiled for sm_100a with nvcc defaults) on the GPU"},
                     iter_ms=iter_ms / it_steps,
                     instances=st.num_rendered, requested_gpus=ref_world)
-        print(json.dumps(line))
+        emit(json.dumps(line))
         return 0
 
     # ------------------------------------------------------------------ ours
@@ -415,7 +431,10 @@ def main():
         # scales 3, rotations 4 = 16 floats per Gaussian — plus the 16 camera sums.  The backward kernels
         # write straight into views of it (no packing copies); it is all-reduced over NVLink inside the step.
         P = P_GAUSS
-        bucket = torch.empty(16 * P + 16, dtype=torch.float32, device=dev)
+        from eogs2_b200.nvls import make_grad_exchange
+        # the exchange is the library's own NVLS kernel (multimem.ld_reduce + multimem.st on a symmetric-memory bucket)
+        # or ncclAllReduce, whichever a short calibration finds faster on this box; named in config["allreduce"]
+        bucket, exchange, exchange_name = make_grad_exchange(16 * P + 16, dev)
         views = {"means3D": bucket[0:3 * P].view(P, 3), "colors": bucket[3 * P:8 * P].view(P, 5),
                  "opacity": bucket[8 * P:9 * P].view(P, 1), "scales": bucket[9 * P:12 * P].view(P, 3),
                  "rotations": bucket[12 * P:16 * P].view(P, 4), "cam_sums": bucket[16 * P:]}
@@ -431,8 +450,9 @@ def main():
             return st, g
 
         def post():
-            dist.all_reduce(bucket)
+            exchange()
         run_step = step_dp
+        base["config"]["allreduce"] = exchange_name
     else:
         run_step = step
 
@@ -481,7 +501,9 @@ def main():
     line = dict(base, value=value, ms_per_step=total_ms / args.steps, clocks=clocks,
                 e2e=None if e2e_ms is None else {"value": world * args.steps / (e2e_ms / 1e3), "unit": "renders/s",
                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                gpu_launches=6 * args.steps,   # preprocess, emit, tile ranges, blend fwd, blend bwd, preprocess bwd (CUB sorts/scans not counted)
+                # preprocess, emit, tile ranges, blend fwd, blend bwd, preprocess bwd (+ the NVLS all-reduce kernel when it
+                # is the chosen exchange); CUB sorts / scans and torch's barrier kernels are not counted
+                gpu_launches=(6 + (1 if world > 1 and exchange_name.startswith("own NVLS") else 0)) * args.steps,
                 roofline={"kernel": "blend_bwd_kernel<5>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                           "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_BWD_TRAFFIC, "peak_source": peak_src,
                           "ms_per_launch": bwd_ms, "algorithmic_bytes": bwd_bytes,
@@ -499,7 +521,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
     if rank == 0:
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

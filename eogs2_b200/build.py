@@ -26,7 +26,7 @@ _SUFFIX = os.environ.get("EOGS_LIB_SUFFIX", "")
 _EXTRA_DEFS = os.environ.get("EOGS_NVCC_DEFS", "").split()
 LIB = PKG_DIR / f"libeogs_raster{_SUFFIX}.so"
 BUILD = PKG_DIR / "csrc" / f"build{_SUFFIX}"
-SOURCES = ["cabi.cu", "preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu", "resample.cu", "ssim_loss.cu", "optim.cu", "knn.cu", "dsm.cu"]
+SOURCES = ["cabi.cu", "preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu", "resample.cu", "ssim_loss.cu", "optim.cu", "knn.cu", "dsm.cu", "nvls.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                      "-Xptxas", "-v", "--expt-relaxed-constexpr", "-Wno-deprecated-declarations"]

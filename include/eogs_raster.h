@@ -327,6 +327,13 @@ EOGS_API int eogs_dsm_splat(eogs_stream_t stream, long long N, const double* clo
                             double resolution, int xsize, int ysize, int radius, float sigma,
                             double* accum, float* raster);
 
+/* ---- NVLS gradient all-reduce (data parallel over views) --------------------------- */
+/* In-switch all-reduce (SUM, fp32) of a bucket that lives in symmetric memory mapped to one multicast address on all
+ * ranks: this rank reduces its 1/world slice with multimem.ld_reduce and broadcasts it with multimem.st.  The caller
+ * brackets the call with cross-GPU barriers (before: all ranks' gradients written; after: all slices landed).
+ *   multicast_ptr: the multicast mapping of the bucket (NULL -> error: fall back to NCCL); n_floats % 4 == 0 */
+EOGS_API int eogs_nvls_allreduce(eogs_stream_t stream, void* multicast_ptr, unsigned long long n_floats, int rank, int world);
+
 /* ---- markVisible ------------------------------------------------------------------- */
 /* The reference's in_frustum culls nothing for affine cameras (its body is
  * commented out, auxiliary.h:151-176): every Gaussian is reported visible. */

@@ -1,0 +1,36 @@
+"""GPU (>= 2 devices on one NVSwitch domain; skipped otherwise): the NVLS all-reduce kernel (csrc/nvls.cu,
+eogs2_b200/nvls.py) equals ncclAllReduce on the same data and every rank ends with the same bucket.
+Runs tools/nvls_check.py under torchrun on 2 ranks."""
+import json
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_nvls_allreduce_matches_nccl_on_two_ranks():
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(ROOT / "tools" / "nvls_check.py")],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    out = json.loads(line)
+    if not out["nvls"]:
+        pytest.skip("NVLS multicast not available on this box")
+    assert out["max_rel_err_vs_nccl"] <= 1e-6
+
+
+def test_no_multicast_pointer_is_an_error_not_a_fallback(cuda_dev):
+    import ctypes as C
+    from eogs2_b200 import _cabi
+    lib = _cabi.load()
+    rc = lib.eogs_nvls_allreduce(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(None), 1024, 0, 2)
+    assert rc != 0 and b"NCCL" in lib.eogs_last_error()
