@@ -494,10 +494,10 @@ def main():
     bwd_ms = stage_ms[STAGES.index("blend_bwd")]
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
     # DRAM traffic of one launch from the committed `ncu --set full` capture of this same command
-    # (profiles/r03n_blend_full.txt: dram__bytes_read.sum 263.80 MB + dram__bytes_write.sum 22.54 MB).  It is far
+    # (profiles/r03y_blend_full.txt: dram__bytes_read.sum 263.80 MB + dram__bytes_write.sum 23.77 MB).  It is far
     # BELOW the algorithmic bytes: records are gathered from L2 (126 MB holds the 48 MB record array) and list
     # entries behind the tile's last contributor are never fetched — the kernel is not HBM-bound.
-    NCU_BWD_TRAFFIC = 263_799_808 + 22_537_984
+    NCU_BWD_TRAFFIC = 263_800_064 + 23_765_760
     line = dict(base, value=value, ms_per_step=total_ms / args.steps, clocks=clocks,
                 e2e=None if e2e_ms is None else {"value": world * args.steps / (e2e_ms / 1e3), "unit": "renders/s",
                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -507,8 +507,8 @@ def main():
                 roofline={"kernel": "blend_bwd_kernel<5>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                           "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_BWD_TRAFFIC, "peak_source": peak_src,
                           "ms_per_launch": bwd_ms, "algorithmic_bytes": bwd_bytes,
-                          "traffic_source": "profiles/r03n_blend_full.txt (ncu --set full, same workload)",
-                          "issue_active_pct_ncu": 63.8,
+                          "traffic_source": "profiles/r03y_blend_full.txt (ncu --set full, same workload)",
+                          "issue_active_pct_ncu": 63.7,
                           "note": "issue-bound, not HBM-bound: ncu smsp__issue_active 64 % with 16 resident warps/SM "
                                   "(register + shared-memory limited), DRAM throughput 2 % of peak; the HBM fraction is "
                                   "reported because the contract asks for it, the binding ceiling is the issue rate "
