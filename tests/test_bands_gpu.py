@@ -115,3 +115,17 @@ def test_bad_band_is_rejected(cuda_dev):
         fwd(c, 64, 64, band=(2, 9))
     with pytest.raises(Exception):
         fwd(c, 64, 64, band=(3, 3))
+
+
+def test_forward_strips_equals_the_single_call_above_65536_tiles(cuda_dev):
+    """4112 x 4112 = 257 x 257 tiles (> 65 536: the single call sorts 32-bit keys, the strips 16-bit ones)."""
+    W = H = 4112
+    c = case(cuda_dev, 20_000, W, H, 31)
+    full = fwd(c, W, H)
+    empty = torch.empty(0, device=cuda_dev)
+    color, invd, radii = B.forward_strips(c["bg"], c["means3D"], c["colors"], c["opacities"], c["scales"],
+                                          c["rotations"], 1.0, empty, c["view"], H, W)
+    assert torch.equal(color, full.color) and torch.equal(invd, full.invdepth) and torch.equal(radii, full.radii)
+    color2, _, _ = B.forward_strips(c["bg"], c["means3D"], c["colors"], c["opacities"], c["scales"], c["rotations"],
+                                    1.0, empty, c["view"], H, W, max_tiles=257 * 40)
+    assert torch.equal(color2, full.color)
