@@ -62,10 +62,7 @@ if bucket is not None:
     def barriers_only():
         bucket.handle.barrier(channel=0, timeout_ms=20000); bucket.handle.barrier(channel=1, timeout_ms=20000)
     out["barriers_ms"] = timeit(barriers_only)
-    for nb in (148, 296, 592, 1184, 2368):
-        os.environ["EOGS_NVLS_BLOCKS"] = str(nb)
-        out[f"kernel_ms_{nb}"] = timeit(kernel_only)
-    os.environ.pop("EOGS_NVLS_BLOCKS")
+    out["kernel_ms"] = timeit(kernel_only)
     out["bytes"] = 4 * n
 if rank == 0:
     print(json.dumps(out))
