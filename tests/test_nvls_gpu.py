@@ -26,6 +26,7 @@ def test_nvls_allreduce_matches_nccl_on_two_ranks():
     if not out["nvls"]:
         pytest.skip("NVLS multicast not available on this box")
     assert out["max_rel_err_vs_nccl"] <= 1e-6
+    assert out["grad_bucket_auto"]["ok"]
 
 
 def test_no_multicast_pointer_is_an_error_not_a_fallback(cuda_dev):

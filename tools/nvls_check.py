@@ -64,6 +64,22 @@ if bucket is not None:
     out["barriers_ms"] = timeit(barriers_only)
     out["kernel_ms"] = timeit(kernel_only)
     out["bytes"] = 4 * n
+# the data-parallel harness with the calibrated exchange (dp.GradBucket(exchange="auto")): 14 P + 16 floats, padded
+from eogs2_b200 import dp      # noqa: E402
+gp = torch.Generator(device=dev).manual_seed(7)
+shapes = {"xyz": 3, "f_dc": 3, "opacity": 1, "scaling": 3, "rotation": 4}
+params = {k: torch.randn(1001, w, device=dev, generator=gp).requires_grad_(True) for k, w in shapes.items()}
+cam = torch.zeros(4, 4, device=dev, requires_grad=True)
+gb = dp.GradBucket(params, {"cam": cam}, exchange="auto")
+for k, p_ in params.items():
+    p_.grad = torch.full_like(p_, float(rank + 1))
+cam.grad = torch.full_like(cam, float(10 * (rank + 1)))
+gb.pack(); gb.all_reduce(); gb.unpack()
+torch.cuda.synchronize()
+tot = world * (world + 1) / 2
+ok = all(bool((p_.grad == tot).all()) for p_ in params.values()) and bool((cam.grad == 10 * tot).all())
+out["grad_bucket_auto"] = {"ok": ok, "exchange": gb.exchange_name, "numel": gb.flat.numel()}
+assert ok, "GradBucket(exchange='auto') did not sum the gradients"
 if rank == 0:
     print(json.dumps(out))
 dist.destroy_process_group()
