@@ -346,7 +346,8 @@ EOGS_API int eogs_mark_visible(eogs_stream_t stream, int P, const float* means3D
  * 1 preprocess, 2 depth sort, 3 scan, 4 emit, 5 tile sort, 6 ranges, 7 blend fwd,
  * 8 bwd zeroing, 9 blend bwd, 10 preprocess bwd; it synchronises the recorded events and
  * returns the number of stages recorded.  The forward render stage continues the timeline
- * of the geometry stage, so the host sync between them is attributed to stage 4 (emit). */
+ * of the geometry stage, so any gap the host leaves between them is attributed to stage 4 (emit); the copy of the
+ * instance count to the host sits in stage 2 (it is enqueued before the depth sort). */
 EOGS_API int eogs_profile_enable(int on);
 EOGS_API int eogs_profile_read(float* ms, int n);
 
