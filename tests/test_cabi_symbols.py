@@ -62,3 +62,19 @@ def test_python_surface_matches_reference_names():
     assert list(sig.parameters) == ["self", "means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
                                     "rotations", "cov3D_precomp"]          # DGR __init__.py:250-260
     assert hasattr(d.GaussianRasterizer, "markVisible") and callable(d.rasterize_gaussians)
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++ types in the signatures) and a C program
+    must link against the shared library and call the host-only entry points."""
+    from eogs2_b200 import _cabi
+    src = tmp_path / "use.c"
+    src.write_text('#include <stdio.h>\n#include "eogs_raster.h"\n'
+                   'int main(void) { printf("%d %zu %zu\\n", eogs_abi_version(), eogs_geom_bytes(1000), eogs_knn_bytes(1000)); return 0; }\n')
+    exe = tmp_path / "use"
+    lib_dir = str(_cabi.LIB_PATH.parent)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}", str(src), "-o", str(exe),
+           f"-L{lib_dir}", "-leogs_raster", f"-Wl,-rpath,{lib_dir}"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == _cabi.ABI_VERSION and int(out[1]) > 0 and int(out[2]) > 0
