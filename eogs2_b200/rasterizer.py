@@ -81,11 +81,16 @@ def _info_host(device: torch.device) -> torch.Tensor:
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     t = _pinned_info.get(key)
     if t is None:
-        t = torch.zeros(4, dtype=torch.int32).pin_memory()          # eogs_forward_info: I, error, ready, reserved
-        t = (t, t.numpy())                 # the numpy view reads the pinned words without a torch dispatch
+        buf = torch.zeros(4, dtype=torch.int32).pin_memory()        # eogs_forward_info: I, error, ready, reserved
+        t = [buf, buf.numpy(), False]      # the numpy view reads the pinned words without a torch dispatch
         _pinned_info[key] = t
+    if t[2]:
+        # the previous call on this stream never collected its words (it raised in between): its copy may still be
+        # in flight and would raise `ready` for THIS call — let it land first
+        torch.cuda.current_stream(device).synchronize()
+    t[2] = True
     t[1][2] = 0                            # `ready` is raised by the device -> host copy of this call
-    return t
+    return t[0], t[1]
 
 
 def _wait_info(info_np, device: torch.device):
@@ -101,6 +106,9 @@ def _wait_info(info_np, device: torch.device):
         torch.cuda.current_stream(device).synchronize()
         if info_np[2] == 0:
             raise _cabi.EogsRasterError("geometry stage finished without publishing its instance count")
+    entry = _pinned_info.get((device.index, torch.cuda.current_stream(device).cuda_stream))
+    if entry is not None:
+        entry[2] = False                   # collected
     return int(info_np[0]) & 0xFFFFFFFF, int(info_np[1])
 
 
