@@ -73,3 +73,24 @@ def test_module_and_helpers(cuda_dev):
     assert abs(float(L.ssim(img, gt)) - float(ref_ssim(img, gt))) < 1e-5
     with pytest.raises(Exception):
         L.photometric_loss(img.cpu(), gt.cpu())
+
+
+def test_fused_loss_against_the_reference_golden(cuda_dev):
+    """tests/golden/loss_ref.npz: outputs of the reference's own loss_utils.py / photometric_L (CPU run)."""
+    import importlib.util
+    from pathlib import Path
+    here = Path(__file__).resolve().parent
+    spec = importlib.util.spec_from_file_location("make_golden_loss", here / "golden" / "make_golden_loss.py")
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    g = np.load(here / "golden" / "loss_ref.npz")
+    for name, (C, H, W, lam, seed) in mg.CASES.items():
+        img = torch.from_numpy(g[f"{name}_image"]).to(cuda_dev).requires_grad_(True)
+        gt = torch.from_numpy(g[f"{name}_gt"]).to(cuda_dev)
+        loss, ssim_mean, l1_mean = L.photometric_loss(img, gt, lam, return_parts=True)
+        loss.backward()
+        want = g[f"{name}_out"]
+        assert abs(float(loss.detach()) - want[0]) <= 1e-5, name
+        assert abs(float(ssim_mean) - want[1]) <= 1e-5 and abs(float(l1_mean) - want[2]) <= 1e-6, name
+        ref_grad = g[f"{name}_grad"]
+        err = np.linalg.norm(img.grad.cpu().numpy() - ref_grad) / np.linalg.norm(ref_grad)
+        assert err < 1e-4, (name, err)
