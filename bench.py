@@ -306,16 +306,24 @@ def cpu_baseline(wl, seconds_hint=20.0):
     torch.set_num_threads(cores)
     sc = wl["sc"]
     gx = IMG // 16
-    win = 6                                            # 6x6 = 36 of 16384 tiles
-    tw = (gx // 2 - win // 2, gx // 2 - win // 2, gx // 2 + win // 2, gx // 2 + win // 2)
     tens = (sc.means3D, sc.scales, sc.rotations, sc.opacities, wl["host"]["colors"])
-    t0 = time.perf_counter()
-    CS.render_fwd_bwd(tens, wl["view_host"], wl["bg"].cpu(), IMG, IMG, wl["dcol"].cpu(), None, False, tile_window=(0, 0, 0, 0))
-    t_geom = time.perf_counter() - t0                  # per-Gaussian work + sort + autograd of it, no tiles
-    t0 = time.perf_counter()
-    CS.render_fwd_bwd(tens, wl["view_host"], wl["bg"].cpu(), IMG, IMG, wl["dcol"].cpu(), None, False, tile_window=tw)
-    t_win = time.perf_counter() - t0
+    bg_c, dcol_c = wl["bg"].cpu(), wl["dcol"].cpu()
+
+    def window(win):
+        tw = (gx // 2 - win // 2, gx // 2 - win // 2, gx // 2 + win // 2, gx // 2 + win // 2) if win else (0, 0, 0, 0)
+        t0 = time.perf_counter()
+        CS.render_fwd_bwd(tens, wl["view_host"], bg_c, IMG, IMG, dcol_c, None, False, tile_window=tw)
+        return time.perf_counter() - t0
+    t_geom = window(0)                                 # per-Gaussian work + sort + autograd of it, no tiles
+    win = 6                                            # probe: 6x6 = 36 of 16384 tiles
+    t_win = window(win)
     per_tile = max(t_win - t_geom, 1e-6) / (win * win)
+    # the sample proper: a central window sized for about `seconds_hint` of CPU work (bounded: 64x64 tiles)
+    big = min(64, int((0.6 * seconds_hint / per_tile) ** 0.5) // 2 * 2)
+    if big > win + 2:
+        win = big
+        t_win = window(win)
+        per_tile = max(t_win - t_geom, 1e-6) / (win * win)
     est = t_geom + per_tile * gx * gx
     return {"value": 1.0 / est, "unit": "renders/s", "cores": cores, "kind": "port",
             "sample": f"oracle/cpu_splat.py (PyTorch CPU, fp32, autograd): all 1M Gaussians preprocessed+sorted "
