@@ -78,3 +78,35 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert int(out[0]) == _cabi.ABI_VERSION and int(out[1]) > 0 and int(out[2]) > 0
+
+
+def declared_parameters():
+    """name -> list of parameter declarations, parsed from the header."""
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"EOGS_API\s+[\w\s\*]+?\b(eogs_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        out[m.group(1)] = [] if params == ["void"] else params
+    return out
+
+
+def test_ctypes_signatures_follow_the_header():
+    """Every binding has as many arguments as the C declaration, pointers are bound as pointers and scalars as the
+    matching ctypes scalar — a drifted ctypes table corrupts the call silently."""
+    import ctypes as C
+    from eogs2_b200 import _cabi
+    decl = declared_parameters()
+    assert sorted(decl) == sorted(_cabi.SIGNATURES)
+    scalar = {"int": C.c_int, "float": C.c_float, "double": C.c_double, "uint32_t": C.c_uint32, "size_t": C.c_size_t,
+              "long long": C.c_longlong, "unsigned long long": C.c_ulonglong}
+    for name, params in decl.items():
+        res, args = _cabi.SIGNATURES[name]
+        assert len(args) == len(params), (name, len(args), params)
+        for a, p in zip(args, params):
+            is_ptr = "*" in p or p.startswith("eogs_stream_t") or p.startswith("eogs_alloc_fn")
+            if is_ptr:
+                assert a in (C.c_void_p, C.c_char_p) or hasattr(a, "contents") or issubclass(a, C._CFuncPtr) \
+                    or a.__name__.startswith("LP_"), (name, p, a)
+            else:
+                ctype = " ".join(p.replace("const ", "").split()[:-1])
+                assert scalar.get(ctype) is a, (name, p, a)
