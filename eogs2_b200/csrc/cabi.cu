@@ -264,7 +264,7 @@ EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, i
     if (!*geom || !*image) { set_error("allocation callback returned NULL"); return -5; }
     // the info words live in the tail of the geometry buffer
     eogs_forward_info* info_dev = reinterpret_cast<eogs_forward_info*>(static_cast<char*>(*geom) + eogs_geom_bytes(P));
-    eogs_forward_info info_host = {0u, 0u};
+    eogs_forward_info info_host = {0u, 0u, 0u, 0u};
     if (int rc = eogs_forward_geometry(stream, P, W, H, channels, means3D, scales, rotations, cov3D_precomp,
                                        opacities, colors, viewmatrix, scale_modifier, antialiasing, radii,
                                        *geom, info_dev, nullptr)) return rc;
