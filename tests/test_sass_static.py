@@ -1,0 +1,71 @@
+"""CPU (needs cuobjdump from the CUDA toolkit, no GPU): static properties of the built sm_100a library that the
+design relies on and that a refactor could silently lose — packed FFMA2/FMUL2 in both blend kernels, cp.async
+(LDGSTS) record staging, mbarrier (SYNCS) in the forward, one red.global per flush in the backward, the
+multimem load-reduce (LDGMC) in the NVLS all-reduce, no local-memory spills in the hot kernels."""
+import re
+import shutil
+import subprocess
+from collections import Counter
+
+import pytest
+
+cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+@pytest.fixture(scope="module")
+def kernels():
+    from eogs2_b200 import _cabi, build
+    build.build()
+    try:
+        sass = subprocess.run([cuobjdump, "-sass", str(_cabi.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    except (OSError, subprocess.CalledProcessError):
+        pytest.skip("cuobjdump not available")
+    out, cur = {}, None
+    for ln in sass.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            out[cur] = Counter()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", ln)
+        if m and cur:
+            out[cur][m.group(1)] += 1
+    return out
+
+
+def find(kernels, fragment):
+    hits = [c for name, c in kernels.items() if fragment in name]
+    assert hits, fragment
+    return hits
+
+
+def test_library_targets_sm_100a_only():
+    from eogs2_b200 import _cabi
+    elf = subprocess.run([cuobjdump, "-lelf", str(_cabi.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", elf))
+    assert archs == {"100a"}, archs
+
+
+def test_blend_kernels_use_packed_fp32x2_and_async_staging(kernels):
+    for c in find(kernels, "blend_fwd_kernelILi5"):
+        assert c["FFMA2"] >= 8 and c["FMUL2"] >= 8, c          # per-pair arithmetic on pixel pairs
+        assert c["LDGSTS"] >= 3                                 # cp.async record staging
+        assert c["SYNCS"] >= 2                                  # mbarrier arrive / try_wait
+    for c in find(kernels, "blend_bwd_kernelILi5"):
+        assert c["FFMA2"] >= 60 and c["FMUL2"] >= 30, c
+        assert c["LDGSTS"] >= 4
+        assert c["REDG"] == 1 and c["ATOMG"] == 0               # ONE red.global per (tile, Gaussian) flush, no returning atomics
+        assert c["SHFL"] <= 16                                  # transposing butterfly: 13 shuffles for 11 values
+        assert c["BAR"] == 0                                    # warp-synchronous: no block barrier at all
+
+
+def test_no_local_memory_in_hot_kernels(kernels):
+    for frag in ("blend_fwd_kernel", "blend_bwd_kernel", "knn_search_kernel", "preprocess_bwd_kernel"):
+        for c in find(kernels, frag):
+            assert c["LDL"] == 0 and c["STL"] == 0, (frag, c["LDL"], c["STL"])
+
+
+def test_nvls_allreduce_uses_multimem(kernels):
+    for c in find(kernels, "nvls_allreduce_kernel"):
+        assert c["LDGMC"] >= 1                                  # multimem.ld_reduce
+        assert c["STG"] >= 1 and c["ATOMG"] == 0 and c["REDG"] == 0
