@@ -76,3 +76,20 @@ def test_grad_viewmatrix_assembly_matches_reference_formula():
     cam_sums[12:14] = grad_means2D[:, :2].sum(0)
     mine = E.assemble_grad_viewmatrix(cam_sums, view, W, H)
     assert torch.allclose(mine, ref, rtol=1e-5, atol=1e-4)
+
+
+def test_product_packages_never_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under eogs2_b200/ or the two shim packages may import it."""
+    import ast
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    for pkg in ("eogs2_b200", "diff_gaussian_rasterization", "simple_knn"):
+        for py in (root / pkg).rglob("*.py"):
+            tree = ast.parse(py.read_text())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n == "oracle" or n.startswith("oracle.") for n in names), (py, names)
