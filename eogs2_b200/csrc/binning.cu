@@ -61,6 +61,9 @@ ImageLayout image_layout(int W, int H, Band band) {
     L.final_T = take(n * 4);
     L.n_contrib = take(n * 4);
     L.ranges = take(tiles * 8);
+    L.tile_work = take(tiles * 4);
+    L.tile_order = take(tiles * 4);
+    L.sched = take(16);
     L.total = off;
     return L;
 }

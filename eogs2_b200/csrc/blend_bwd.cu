@@ -22,8 +22,11 @@
 //             "colour behind" dot product and the 11 accumulators.  Per-pixel constants
 //             (dL_dpixel, T_final * bg.dL_dpixel) live in shared memory, lane-contiguous
 //             (conflict-free LDS.128), the dynamic state (T, accum, n_contrib) in registers.
-//   flush     transposing butterfly over the 32 lanes -> lane with slot k holds total k ->
-//             one red.global.add.f32 warp instruction into the Gaussian's 64-byte record.
+//   flush     the 6+C per-lane partial sums cross the warp through shared memory: 11 conflict-free STS
+//             ([value][lane]), then lane (k, h) adds half a row (4 x LDS.128, packed adds), one shuffle
+//             joins the halves and lanes 0..10 issue ONE red.global.add.f32 warp instruction into the
+//             Gaussian's 64-byte record.  (The transposing shuffle butterfly it replaces — 13 SHFL + 22
+//             FSEL + 24 FADD, five dependent levels — was 24 % of the kernel's stall samples, ncu r2a.)
 //
 // Other differences from the reference kernel (unchanged from the first version)
 //   - the replay starts at the tile's max(n_contrib): entries nobody blended are never fetched;
@@ -48,6 +51,7 @@ static_assert(BWD_WX * BWD_WY == BWD_WARPS, "EOGS_BWD_WARPS must be 1, 2 or 4");
 constexpr int BWD_THREADS = BWD_WARPS * 32;
 constexpr int NPATCH = (TILE / PATCH_W) * (TILE / PATCH_H);   // 8
 constexpr int NSTRIP = NPATCH / 2;           // 4 strips of 16x4 pixels = a left and a right patch
+constexpr int RED_STRIDE = 36;
 
 // Accuracy switches for A/B builds (tools/fuzz_check.py): accurate expf / IEEE division instead of
 // ex2.approx / rcp.approx for the VALUES (the accept decision never depends on them, see alpha_cut).
@@ -61,6 +65,28 @@ constexpr int NSTRIP = NPATCH / 2;           // 4 strips of 16x4 pixels = a left
 #ifndef EOGS_BWD_STATE_SMEM
 #define EOGS_BWD_STATE_SMEM 0                // 1: T / accum in shared memory (-16 registers, +2 LDS/STS per strip)
 #endif
+// 1: persistent warps.  Every warp pulls the next tile from a global queue (one atomicAdd per tile) that the
+// forward ordered longest-first (tile_order_kernel below: descending max(n_contrib), tiles nobody blended left
+// out).  A warp replays ~7 tiles per launch at the bench size and a heavy tile costs several average ones, so
+// the static tile -> CTA map left 15 % of the warp slots idle (ncu sm__warps_active 13.6 of 16: a CTA kept its
+// registers until its slowest warp finished, and the last CTAs of the grid ran alone).  0: one warp per tile of
+// a 2x2 block, static grid.
+#ifndef EOGS_BWD_PERSIST
+#define EOGS_BWD_PERSIST 1
+#endif
+// 1: stage A only for the half tiles (strips 0-1 / 2-3) the entry's patch mask reaches.
+#ifndef EOGS_BWD_HALF_SKIP
+#define EOGS_BWD_HALF_SKIP 1
+#endif
+// 1: cross-lane reduction of the flush through shared memory (see "flush" above); 0: transposing shuffle butterfly.
+#ifndef EOGS_BWD_SMEM_FLUSH
+#define EOGS_BWD_SMEM_FLUSH 1
+#endif
+// 1: stage B runs strip PAIRS as straight-line code when both strips are live (two independent dependency
+// chains for the scheduler to interleave); 0: one strip per uniform branch.
+#ifndef EOGS_BWD_PAIR_ILP
+#define EOGS_BWD_PAIR_ILP 0
+#endif
 
 // Per-pixel constants of a lane's pixel PAIR in strip r (left patch 2r, right patch 2r+1), laid out
 // as the f32x2 operands the replay consumes: an LDS.128 lands two ready-made register pairs.
@@ -68,6 +94,10 @@ struct BwdWarpSmem {
     float4 rec[2][32][REC_F4];        // two stages of 32 packed records (cp.async destinations, 48 B each)
     uint32_t rid[2][32];              // Gaussian id of each staged record
     float cut[2][32];                 // alpha_cut of each staged record: accept iff power >= cut
+    int pmax[NPATCH];                 // max(n_contrib) over each 8x4 patch (warp-uniform; read once per batch)
+#if EOGS_BWD_SMEM_FLUSH
+    float red[6 + EOGS_MAX_CHANNELS][RED_STRIDE];   // flush: [value][lane], rows padded to 36 floats (LDS.128 of 8 lanes hit 8 bank groups)
+#endif
     float4 pix[NSTRIP][4][32];        // [0] = {g0.L, g0.R, g1.L, g1.R}   [1] = {g2.L, g2.R, g3.L, g3.R}
                                       // [2] = {g4.L, g4.R, ginv.L, ginv.R}
                                       // [3] = {-T_final (bg . g).L, same .R, n_contrib.L, n_contrib.R (int bits)}
@@ -85,7 +115,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  int tiles_x, int tiles_y, int band_row0, int band_h,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, const float* __restrict__ dL_dinvdepth,
-                 float* __restrict__ grad_rec)
+                 float* __restrict__ grad_rec,
+                 const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ sched, uint32_t* queue)
 {
     constexpr int NV = 6 + C;   // mean2D.xy, conic.xyw, opacity, colours
     constexpr uint32_t FULL = 0xffffffffu;
@@ -93,244 +124,423 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     BwdWarpSmem* s_warp = reinterpret_cast<BwdWarpSmem*>(s_dyn);
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    // tiles_y = tile rows of the band; brow = row inside the band, tile_y = row in the image
-    const int tile_x = (int)blockIdx.x * BWD_WX + (int)(warp % BWD_WX), brow = (int)blockIdx.y * BWD_WY + (int)(warp / BWD_WX);
-    if (tile_x >= tiles_x || brow >= tiles_y) return;            // whole warp leaves; no block barriers below
-    const int tile_y = brow + band_row0;
     BwdWarpSmem& sm = s_warp[warp];
-
-    const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);
     const float img_x1 = (float)(W - 1), img_y1 = (float)(H - 1);
-    const uint2 range = __ldg(ranges + (size_t)brow * tiles_x + tile_x);
-    const uint32_t* list = point_list + range.x;
-
-    // ---- per-pixel state: pixel (patch p, lane) = (tile_x*16 + 8*(p&1) + (lane&7), tile_y*16 + 4*(p>>1) + (lane>>3))
-    const float pxl = tx0 + (float)(lane & 7u);
-    const f2 neg_px = mk2(-pxl, -(pxl + (float)PATCH_W));       // dx = mean.x - px as an add
-    const float py_lane = ty0 + (float)(lane >> 3);              // + 4r = the strip's pixel row (exact)
 
     float bgv[C];
 #pragma unroll
     for (int ch = 0; ch < C; ch++) bgv[ch] = __ldg(bg + ch);
 
-    int pmax[NPATCH], ncon[NPATCH];
-#if !EOGS_BWD_STATE_SMEM
-    f2 T2[NSTRIP], accum2[NSTRIP];
-#endif
-    int nmax = 0;
-#pragma unroll
-    for (int r = 0; r < NSTRIP; r++) {
-        float g[2][5], g_inv[2], Tf[2], nbg[2];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int p = 2 * r + h;
-            const int px = tile_x * TILE + PATCH_W * h + (int)(lane & 7u);
-            const int py = tile_y * TILE + PATCH_H * r + (int)(lane >> 3);
-            const bool inside = px < W && py < H;
-            const size_t pix_id = (size_t)(py - band_row0 * TILE) * W + px;     // band-compact buffers
-            ncon[p] = inside ? (int)__ldg(n_contrib + pix_id) : 0;
-            Tf[h] = inside ? __ldg(final_T + pix_id) : 0.f;
-            float bg_dot_g = 0.f;
-#pragma unroll
-            for (int ch = 0; ch < 5; ch++) {
-                g[h][ch] = (ch < C && inside) ? __ldg(dL_dpix + (size_t)ch * band_h * W + pix_id) : 0.f;
-                if (ch < C) bg_dot_g = fmaf(bgv[ch], g[h][ch], bg_dot_g);
-            }
-            g_inv[h] = (inside && dL_dinvdepth) ? __ldg(dL_dinvdepth + pix_id) : 0.f;
-            nbg[h] = -Tf[h] * bg_dot_g;
-            pmax[p] = __reduce_max_sync(FULL, ncon[p]);
-            nmax = max(nmax, pmax[p]);
-        }
-        sm.pix[r][0][lane] = make_float4(g[0][0], g[1][0], g[0][1], g[1][1]);
-        sm.pix[r][1][lane] = make_float4(g[0][2], g[1][2], g[0][3], g[1][3]);
-        sm.pix[r][2][lane] = make_float4(g[0][4], g[1][4], g_inv[0], g_inv[1]);
-        sm.pix[r][3][lane] = make_float4(nbg[0], nbg[1], 0.f, 0.f);
-#if EOGS_BWD_STATE_SMEM
-        sm.state[r][lane] = make_float4(Tf[0], Tf[1], 0.f, 0.f);
+#if EOGS_BWD_SMEM_FLUSH
+    const int red_k = (int)(lane % NV), red_h = (int)(lane / NV);   // lane (k, h) adds columns [16h, 16h+16) of row k
+    const int my_slot = lane < (uint32_t)NV ? (int)lane : -1;
 #else
-        T2[r] = mk2(Tf[0], Tf[1]);
-        accum2[r] = bc2(0.f);
-#endif
-    }
-    if (nmax == 0) return;                     // entries [nmax, n) were blended by no pixel of this tile
-    const int rounds = (nmax + 31) >> 5;
-
-    // Batch b, lane l holds list position nmax-1 - (32 b + l): back to front.  Records travel
-    // global -> shared with cp.async (no staging registers), one batch ahead of the replay.
-    uint32_t id_next = 0;
-    {
-        const int p0 = nmax - 1 - (int)lane;
-        if (p0 >= 0) {
-            const uint32_t id = __ldg(list + p0);
-            sm.rid[0][lane] = id;
-            const float4* src = splat + (size_t)id * REC_F4;
-#pragma unroll
-            for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[0][lane][k], src + k);
-            cp_async4(&sm.cut[0][lane], alpha_cut + id);
-        }
-        cp_async_commit();
-        if (p0 - 32 >= 0) id_next = __ldg(list + p0 - 32);
-    }
     const int my_slot = fold_slot<NV>(lane);
+#endif
     // The accumulators are kept un-scaled and un-signed; the constant factors of each gradient slot
-    // are applied once per flush: mean2D gets -d(pixel)/d(ndc), the conic terms -1/2.
+    // are applied once per flush: mean2D gets -d(pixel)/d(ndc), the conic terms -1/2 (and the opacity, below).
     const float slot_scale = my_slot == 0 ? -0.5f * (float)W : my_slot == 1 ? -0.5f * (float)H :
                              (my_slot >= 2 && my_slot <= 4) ? -0.5f : 1.f;
+    const bool slot_takes_op = my_slot >= 2 && my_slot <= 4;
 
-    int first = nmax - 1;                      // list position held by lane 0 in this batch
-    for (int i = 0; i < rounds; i++, first -= 32) {
-        const int pos = first - (int)lane;
-        const int stage = i & 1;
-        cp_async_wait<0>();                    // this lane's record of batch i has landed
-        uint32_t m = 0u;
-        if (pos >= 0) m = patch_mask(sm.rec[stage][lane][0], sm.rec[stage][lane][1], tx0, ty0, img_x1, img_y1);
-#pragma unroll
-        for (int p = 0; p < NPATCH; p++)
-            if (pos >= pmax[p]) m &= ~(1u << p);               // every pixel of patch p stopped before pos
-        uint32_t todo = __ballot_sync(FULL, m != 0u);
-        __syncwarp();                          // all lanes' records visible; previous batch's stage is free
-
-        // next batch's records are in flight while this one is replayed
-        if (pos - 32 >= 0) {
-            sm.rid[stage ^ 1][lane] = id_next;
-            const float4* src = splat + (size_t)id_next * REC_F4;
-#pragma unroll
-            for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[stage ^ 1][lane][k], src + k);
-            cp_async4(&sm.cut[stage ^ 1][lane], alpha_cut + id_next);
-        }
-        cp_async_commit();
-        if (pos - 64 >= 0) id_next = __ldg(list + pos - 64);
-
-        while (todo) {
-            const int e = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const uint32_t me = __shfl_sync(FULL, m, e);
-            const int pos_e = first - e;
-            const float4 ra = sm.rec[stage][e][0];     // mean.x, mean.y, conic.x, conic.y
-            const float4 rb = sm.rec[stage][e][1];     // conic.z, opacity, c0, c1
-            const float4 rc = sm.rec[stage][e][2];     // c2, c3, c4, 1/depth
-            const float col[5] = {rb.z, rb.w, rc.x, rc.y, rc.z};
-            const float cut_e = sm.cut[stage][e];      // the forward accepted a pixel of this entry iff power >= cut_e
-
-            f2 v2[NV];
-#pragma unroll
-            for (int k = 0; k < NV; k++) v2[k] = bc2(0.f);
-            bool any;
-
-            // the forward's exponent in its op order (pair_power), on the lane's (left, right) pixel pair
-            const f2 dx2 = add2(bc2(ra.x), neg_px);
-            const f2 zdx2 = mul2(bc2(ra.z), dx2);
-            const f2 wdx2 = mul2(bc2(ra.w), dx2);
-
-            // One 16x4 strip per step = one pixel PAIR per lane, all arithmetic packed (FFMA2).  Written
-            // branch-free: a rejected pixel runs the same arithmetic with alpha = G = 0, which leaves T,
-            // accum and every accumulator unchanged.  A patch whose mask bit is clear cannot be accepted
-            // (the mask is conservative), so the bits only decide whether the strip is visited at all.
-            // Stage A, all four strips up front and branch-free: G, alpha and the accept test of the lane's
-            // 8 pixels depend only on geometry, never on the replay state, so the four chains
-            // (FFMA2 -> ex2 -> min -> compare) are independent and overlap each other's latency.
-            f2 a2[NSTRIP], Gv2[NSTRIP];
-            uint32_t live = 0u;                                   // bit r: some pixel of strip r accepts this entry
-#pragma unroll
-            for (int r = 0; r < NSTRIP; r++) {
-                const float dy = __fsub_rn(ra.y, py_lane + (float)(PATCH_H * r));
-                const float cyy = __fmul_rn(__fmul_rn(rb.x, dy), dy);
-                const f2 quad2 = fma2(dx2, zdx2, bc2(cyy));
-                const f2 power2 = fma2(quad2, bc2(-0.5f), mul2(wdx2, bc2(-dy)));
-                // exp through ex2.approx (relative error ~2^-22): the VALUES carry a 1e-3 bar.  The accept
-                // DECISION alpha >= 1/255 must be the forward's, or a pixel on that contour flips and a whole
-                // term appears / disappears (1e-3..1e-2 in small scenes, tools/fuzz_parity.py).  It is taken on
-                // the exponent instead: power >= alpha_cut, the per-Gaussian threshold the preprocess derived
-                // from the forward's own expf (geom_math.cuh: alpha_cut_of) — same decision, same instruction count.
-#if EOGS_BWD_EXACT_EXP
-                const float G0 = expf(lo2(power2)), G1 = expf(hi2(power2));
+#if EOGS_BWD_PERSIST
+    const uint32_t n_active = __ldg(sched);                      // tiles with max(n_contrib) > 0, longest first
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(queue, 1u);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= n_active) break;
+        const uint32_t tile = __ldg(tile_order + q);
+        const int tile_x = (int)(tile % (uint32_t)tiles_x), brow = (int)(tile / (uint32_t)tiles_x);
+        (void)tiles_y;
 #else
-                const f2 pl2 = mul2(power2, bc2(1.4426950408889634f));
-                const float G0 = ex2_approx(lo2(pl2)), G1 = ex2_approx(hi2(pl2));
+    {
+        (void)tile_order; (void)sched; (void)queue;
+        // tiles_y = tile rows of the band; brow = row inside the band, tile_y = row in the image
+        const int tile_x = (int)blockIdx.x * BWD_WX + (int)(warp % BWD_WX), brow = (int)blockIdx.y * BWD_WY + (int)(warp / BWD_WX);
+        if (tile_x >= tiles_x || brow >= tiles_y) return;        // whole warp leaves; no block barriers below
 #endif
-                const f2 og2 = mul2(bc2(rb.y), mk2(G0, G1));
-                const float al0 = fminf(0.99f, lo2(og2)), al1 = fminf(0.99f, hi2(og2));
-                // entry at list position pos_e is blended by a pixel iff pos_e < n_contrib (backward.cu:556-558)
-                const bool v0 = pos_e < ncon[2 * r] && !(lo2(power2) > 0.0f) && !(lo2(power2) < cut_e);
-                const bool v1 = pos_e < ncon[2 * r + 1] && !(hi2(power2) > 0.0f) && !(hi2(power2) < cut_e);
-                a2[r] = mk2(v0 ? al0 : 0.f, v1 ? al1 : 0.f);
-                Gv2[r] = mk2(v0 ? G0 : 0.f, v1 ? G1 : 0.f);
-                if (__any_sync(FULL, v0 || v1)) live |= 1u << r;
-            }
-            (void)me;
-            any = live != 0u;
+        const int tile_y = brow + band_row0;
+        const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);
+        const uint2 range = __ldg(ranges + (size_t)brow * tiles_x + tile_x);
+        const uint32_t* list = point_list + range.x;
 
-            // Stage B: the sequential part (T, accum recurrences).  One 16x4 strip per step = one pixel
-            // PAIR per lane, all arithmetic packed (FFMA2).  Branch-free inside a strip: a rejected
-            // pixel runs the same arithmetic with alpha = G = 0, which leaves T, accum and every
-            // accumulator unchanged.
-#pragma unroll
-            for (int r = 0; r < NSTRIP; r++) {
-                if (!((live >> r) & 1u)) continue;               // warp-uniform
-                const float dy = __fsub_rn(ra.y, py_lane + (float)(PATCH_H * r));
-                const float4 pa = sm.pix[r][0][lane], pb = sm.pix[r][1][lane];
-                const float4 pc = sm.pix[r][2][lane], pd = sm.pix[r][3][lane];
-                const f2 g2[5] = {mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(pb.x, pb.y), mk2(pb.z, pb.w), mk2(pc.x, pc.y)};
-                const f2 ginv2 = mk2(pc.z, pc.w), nbg2 = mk2(pd.x, pd.y);
-#if EOGS_BWD_STATE_SMEM
-                const float4 st = sm.state[r][lane];
-                const f2 Told2 = mk2(st.x, st.y), accum_old2 = mk2(st.z, st.w);
-#else
-                const f2 Told2 = T2[r], accum_old2 = accum2[r];
+        // ---- per-pixel state: pixel (patch p, lane) = (tile_x*16 + 8*(p&1) + (lane&7), tile_y*16 + 4*(p>>1) + (lane>>3))
+        const float pxl = tx0 + (float)(lane & 7u);
+        const f2 neg_px = mk2(-pxl, -(pxl + (float)PATCH_W));   // dx = mean.x - px as an add
+        const float py_lane = ty0 + (float)(lane >> 3);          // + 4r = the strip's pixel row (exact)
+        // dy = mean.y - py as an add, for the strip pairs (0, 1) and (2, 3)
+        const f2 neg_py01 = mk2(-py_lane, -(py_lane + (float)PATCH_H));
+        const f2 neg_py23 = mk2(-(py_lane + (float)(2 * PATCH_H)), -(py_lane + (float)(3 * PATCH_H)));
+
+        int ncon[NPATCH];
+#if !EOGS_BWD_STATE_SMEM
+        f2 T2[NSTRIP], accum2[NSTRIP];
 #endif
-                const f2 om2 = fma2(a2[r], bc2(-1.f), bc2(1.f));                // 1 - alpha
-#if EOGS_BWD_EXACT_DIV
-                const f2 inv2 = mk2(__fdiv_rn(1.f, lo2(om2)), __fdiv_rn(1.f, hi2(om2)));
-#else
-                const f2 inv2 = mk2(fast_rcp(lo2(om2)), fast_rcp(hi2(om2)));    // exactly 1 for a rejected pixel
-#endif
-                const f2 Tn2 = mul2(Told2, inv2);
-                const f2 w2 = mul2(a2[r], Tn2);
-                f2 cg2 = mul2(bc2(rc.w), ginv2);
+        int nmax = 0;
 #pragma unroll
-                for (int ch = 0; ch < C; ch++) {
-                    fma2_acc(v2[6 + ch], w2, g2[ch]);
-                    fma2_acc(cg2, bc2(col[ch]), g2[ch]);
+        for (int r = 0; r < NSTRIP; r++) {
+            float g[2][5], g_inv[2], Tf[2], nbg[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int p = 2 * r + h;
+                const int px = tile_x * TILE + PATCH_W * h + (int)(lane & 7u);
+                const int py = tile_y * TILE + PATCH_H * r + (int)(lane >> 3);
+                const bool inside = px < W && py < H;
+                const size_t pix_id = (size_t)(py - band_row0 * TILE) * W + px;     // band-compact buffers
+                ncon[p] = inside ? (int)__ldg(n_contrib + pix_id) : 0;
+                Tf[h] = inside ? __ldg(final_T + pix_id) : 0.f;
+                float bg_dot_g = 0.f;
+#pragma unroll
+                for (int ch = 0; ch < 5; ch++) {
+                    g[h][ch] = (ch < C && inside) ? __ldg(dL_dpix + (size_t)ch * band_h * W + pix_id) : 0.f;
+                    if (ch < C) bg_dot_g = fmaf(bgv[ch], g[h][ch], bg_dot_g);
                 }
-                // accum = (colour blended behind this entry) . dL_dpixel
-                const f2 behind2 = fma2(accum_old2, bc2(-1.f), cg2);
-                const f2 dLa2 = fma2(nbg2, inv2, mul2(behind2, Tn2));           // dL/dalpha (finite; x0 below if rejected)
-                const f2 acc_new2 = fma2(a2[r], behind2, accum_old2);
+                g_inv[h] = (inside && dL_dinvdepth) ? __ldg(dL_dinvdepth + pix_id) : 0.f;
+                nbg[h] = -Tf[h] * bg_dot_g;
+                const int pm = __reduce_max_sync(FULL, ncon[p]);
+                if (lane == 0) sm.pmax[p] = pm;
+                nmax = max(nmax, pm);
+            }
+            sm.pix[r][0][lane] = make_float4(g[0][0], g[1][0], g[0][1], g[1][1]);
+            sm.pix[r][1][lane] = make_float4(g[0][2], g[1][2], g[0][3], g[1][3]);
+            sm.pix[r][2][lane] = make_float4(g[0][4], g[1][4], g_inv[0], g_inv[1]);
+            sm.pix[r][3][lane] = make_float4(nbg[0], nbg[1], 0.f, 0.f);
 #if EOGS_BWD_STATE_SMEM
-                sm.state[r][lane] = make_float4(lo2(Tn2), hi2(Tn2), lo2(acc_new2), hi2(acc_new2));
+            sm.state[r][lane] = make_float4(Tf[0], Tf[1], 0.f, 0.f);
 #else
-                T2[r] = Tn2; accum2[r] = acc_new2;
+            T2[r] = mk2(Tf[0], Tf[1]);
+            accum2[r] = bc2(0.f);
 #endif
-                const f2 dG2 = mul2(bc2(rb.y), dLa2);                            // dL/dG
-                const f2 gdx2 = mul2(Gv2[r], dx2), gdy2 = mul2(Gv2[r], bc2(dy));
-                fma2_acc(v2[0], dG2, fma2(gdx2, bc2(ra.z), mul2(gdy2, bc2(ra.w))));
-                fma2_acc(v2[1], dG2, fma2(gdy2, bc2(rb.x), mul2(gdx2, bc2(ra.w))));
-                const f2 hgx2 = mul2(dG2, gdx2);
-                fma2_acc(v2[2], hgx2, dx2);
-                fma2_acc(v2[3], hgx2, bc2(dy));
-                fma2_acc(v2[4], mul2(dG2, gdy2), bc2(dy));
-                fma2_acc(v2[5], Gv2[r], dLa2);
-            }
-            if (any) {
-                float v[NV];
-#pragma unroll
-                for (int k = 0; k < NV; k++) v[k] = lo2(v2[k]) + hi2(v2[k]);
-                warp_transpose_reduce<NV>(v, lane);
-                const uint32_t gid = sm.rid[stage][e];
-                if (my_slot >= 0) atomicAdd(grad_rec + (size_t)gid * GRAD_STRIDE + my_slot, v[0] * slot_scale);
-            }
         }
-        __syncwarp();
+#if EOGS_BWD_PERSIST
+        if (nmax == 0) continue;               // (cannot happen for a queued tile; kept for safety)
+#else
+        if (nmax == 0) return;                 // entries [nmax, n) were blended by no pixel of this tile
+#endif
+        const int rounds = (nmax + 31) >> 5;
+
+        // Batch b, lane l holds list position nmax-1 - (32 b + l): back to front.  Records travel
+        // global -> shared with cp.async (no staging registers), one batch ahead of the replay.
+        uint32_t id_next = 0;
+        {
+            const int p0 = nmax - 1 - (int)lane;
+            if (p0 >= 0) {
+                const uint32_t id = __ldg(list + p0);
+                sm.rid[0][lane] = id;
+                const float4* src = splat + (size_t)id * REC_F4;
+#pragma unroll
+                for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[0][lane][k], src + k);
+                cp_async4(&sm.cut[0][lane], alpha_cut + id);
+            }
+            cp_async_commit();
+            if (p0 - 32 >= 0) id_next = __ldg(list + p0 - 32);
+        }
+
+
+        int first = nmax - 1;                  // list position held by lane 0 in this batch
+        for (int i = 0; i < rounds; i++, first -= 32) {
+            const int pos = first - (int)lane;
+            const int stage = i & 1;
+            cp_async_wait<0>();                // this lane's record of batch i has landed
+            uint32_t m = 0u;
+            if (pos >= 0) m = patch_mask(sm.rec[stage][lane][0], sm.rec[stage][lane][1], tx0, ty0, img_x1, img_y1);
+            {
+                const int4 pm0 = *reinterpret_cast<const int4*>(&sm.pmax[0]), pm1 = *reinterpret_cast<const int4*>(&sm.pmax[4]);
+                const int pmv[NPATCH] = {pm0.x, pm0.y, pm0.z, pm0.w, pm1.x, pm1.y, pm1.z, pm1.w};
+#pragma unroll
+                for (int p = 0; p < NPATCH; p++)
+                    if (pos >= pmv[p]) m &= ~(1u << p);        // every pixel of patch p stopped before pos
+            }
+            uint32_t todo = __ballot_sync(FULL, m != 0u);
+            __syncwarp();                      // all lanes' records visible; previous batch's stage is free
+
+            // next batch's records are in flight while this one is replayed
+            if (pos - 32 >= 0) {
+                sm.rid[stage ^ 1][lane] = id_next;
+                const float4* src = splat + (size_t)id_next * REC_F4;
+#pragma unroll
+                for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[stage ^ 1][lane][k], src + k);
+                cp_async4(&sm.cut[stage ^ 1][lane], alpha_cut + id_next);
+            }
+            cp_async_commit();
+            if (pos - 64 >= 0) id_next = __ldg(list + pos - 64);
+
+            while (todo) {
+                const int e = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                const uint32_t me = __shfl_sync(FULL, m, e);
+                const int pos_e = first - e;
+                const float4 ra = sm.rec[stage][e][0];     // mean.x, mean.y, conic.x, conic.y
+                const float4 rb = sm.rec[stage][e][1];     // conic.z, opacity, c0, c1
+                const float4 rc = sm.rec[stage][e][2];     // c2, c3, c4, 1/depth
+                const float col[5] = {rb.z, rb.w, rc.x, rc.y, rc.z};
+                const float cut_e = sm.cut[stage][e];      // the forward accepted a pixel of this entry iff power >= cut_e
+
+                f2 v2[NV];
+#pragma unroll
+                for (int k = 0; k < NV; k++) v2[k] = bc2(0.f);
+
+                // the forward's exponent in its op order (forward.cu:361-365 as compiled: blend_fwd.cu), on the
+                // lane's (left, right) pixel pair; every half of a packed operation rounds like the scalar one,
+                // so `power` has the forward's bits and the accept decision below is the forward's
+                const f2 dx2 = add2(bc2(ra.x), neg_px);
+                const f2 zdx2 = mul2(bc2(ra.z), dx2);
+                const f2 wdx2 = mul2(bc2(ra.w), dx2);
+                const f2 dy01 = add2(bc2(ra.y), neg_py01), dy23 = add2(bc2(ra.y), neg_py23);
+                const f2 cyy01 = mul2(mul2(bc2(rb.x), dy01), dy01), cyy23 = mul2(mul2(bc2(rb.x), dy23), dy23);
+                const float dyv[NSTRIP] = {lo2(dy01), hi2(dy01), lo2(dy23), hi2(dy23)};
+                const float cyyv[NSTRIP] = {lo2(cyy01), hi2(cyy01), lo2(cyy23), hi2(cyy23)};
+
+                // Stage A, branch-free over the strips it covers: G, alpha and the accept test of the lane's
+                // pixels depend only on geometry, never on the replay state, so the chains
+                // (FFMA2 -> ex2 -> select -> min) of the strips are independent and overlap each other's
+                // latency.  A rejected pixel gets G = alpha = 0, which leaves T, accum and every accumulator
+                // unchanged in stage B.  A patch whose mask bit is clear cannot be accepted (the mask is
+                // conservative), so the mask only decides which HALF tiles are evaluated at all.
+                f2 a2[NSTRIP], Gv2[NSTRIP];
+                uint32_t lane_live = 0u;                              // bit r: a pixel of THIS lane in strip r accepts this entry
+                auto stage_a = [&](const int r) {
+                    const f2 quad2 = fma2(dx2, zdx2, bc2(cyyv[r]));
+                    const f2 power2 = fma2(quad2, bc2(-0.5f), mul2(wdx2, bc2(-dyv[r])));
+                    // exp through ex2.approx (relative error ~2^-22): the VALUES carry a 1e-3 bar.  The accept
+                    // DECISION alpha >= 1/255 must be the forward's, or a pixel on that contour flips and a whole
+                    // term appears / disappears (1e-3..1e-2 in small scenes, tools/fuzz_parity.py).  It is taken on
+                    // the exponent instead: power >= alpha_cut, the per-Gaussian threshold the preprocess derived
+                    // from the forward's own expf (geom_math.cuh: alpha_cut_of) — same decision, same instruction count.
+#if EOGS_BWD_EXACT_EXP
+                    const float G0 = expf(lo2(power2)), G1 = expf(hi2(power2));
+#else
+                    const f2 pl2 = mul2(power2, bc2(1.4426950408889634f));
+                    const float G0 = ex2_approx(lo2(pl2)), G1 = ex2_approx(hi2(pl2));
+#endif
+                    // entry at list position pos_e is blended by a pixel iff pos_e < n_contrib (backward.cu:556-558)
+                    const bool v0 = pos_e < ncon[2 * r] && !(lo2(power2) > 0.0f) && !(lo2(power2) < cut_e);
+                    const bool v1 = pos_e < ncon[2 * r + 1] && !(hi2(power2) > 0.0f) && !(hi2(power2) < cut_e);
+                    Gv2[r] = mk2(v0 ? G0 : 0.f, v1 ? G1 : 0.f);       // one select per pixel: alpha follows from G
+                    const f2 og2 = mul2(bc2(rb.y), Gv2[r]);
+                    a2[r] = mk2(fminf(0.99f, lo2(og2)), fminf(0.99f, hi2(og2)));
+                    lane_live |= (v0 || v1) ? (1u << r) : 0u;
+                };
+#if EOGS_BWD_HALF_SKIP
+                const bool top = (me & 0x0Fu) != 0u, bottom = (me & 0xF0u) != 0u;     // warp-uniform
+                if (top && bottom) {
+#pragma unroll
+                    for (int r = 0; r < NSTRIP; r++) stage_a(r);
+                } else if (top) {
+                    stage_a(0); stage_a(1);
+                } else {
+                    stage_a(2); stage_a(3);
+                }
+#else
+                (void)me;
+#pragma unroll
+                for (int r = 0; r < NSTRIP; r++) stage_a(r);
+#endif
+                const uint32_t live = __reduce_or_sync(FULL, lane_live);    // bit r: some pixel of strip r accepts (one REDUX)
+                const bool any = live != 0u;
+
+                // Stage B: the sequential part (T, accum recurrences).  One 16x4 strip per step = one pixel
+                // PAIR per lane, all arithmetic packed (FFMA2).  Branch-free inside a strip.
+                // Per-Gaussian sums kept per lane, with u = G dL/dalpha (so dL/dG = opacity u):
+                //   v2[0] = sum u dx   v2[1] = sum u dy   v2[2] = sum u dx dx   v2[3] = sum u dx dy   v2[4] = sum u dy dy
+                //   v2[5] = sum u      v2[6 + ch] = sum alpha T dL_dpixel[ch]
+                // The conic and the opacity are constants of the entry, so the mean gradient
+                // (backward.cu:631-632: dL_dG dG/ddelta) is assembled from the two first moments at flush time
+                // instead of per pixel: 27 packed operations per strip instead of 33.
+                auto stage_b = [&](const int r) {
+                    const float dy = dyv[r];
+                    const float4 pa = sm.pix[r][0][lane], pb = sm.pix[r][1][lane];
+                    const float4 pc = sm.pix[r][2][lane], pd = sm.pix[r][3][lane];
+                    const f2 g2[5] = {mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(pb.x, pb.y), mk2(pb.z, pb.w), mk2(pc.x, pc.y)};
+                    const f2 ginv2 = mk2(pc.z, pc.w), nbg2 = mk2(pd.x, pd.y);
+#if EOGS_BWD_STATE_SMEM
+                    const float4 st = sm.state[r][lane];
+                    const f2 Told2 = mk2(st.x, st.y), accum_old2 = mk2(st.z, st.w);
+#else
+                    const f2 Told2 = T2[r], accum_old2 = accum2[r];
+#endif
+                    const f2 om2 = fma2(a2[r], bc2(-1.f), bc2(1.f));                // 1 - alpha
+#if EOGS_BWD_EXACT_DIV
+                    const f2 inv2 = mk2(__fdiv_rn(1.f, lo2(om2)), __fdiv_rn(1.f, hi2(om2)));
+#else
+                    const f2 inv2 = mk2(fast_rcp(lo2(om2)), fast_rcp(hi2(om2)));    // exactly 1 for a rejected pixel
+#endif
+                    const f2 Tn2 = mul2(Told2, inv2);
+                    const f2 w2 = mul2(a2[r], Tn2);
+                    f2 cg2 = mul2(bc2(rc.w), ginv2);
+#pragma unroll
+                    for (int ch = 0; ch < C; ch++) {
+                        fma2_acc(v2[6 + ch], w2, g2[ch]);
+                        fma2_acc(cg2, bc2(col[ch]), g2[ch]);
+                    }
+                    // accum = (colour blended behind this entry) . dL_dpixel
+                    const f2 behind2 = fma2(accum_old2, bc2(-1.f), cg2);
+                    const f2 dLa2 = fma2(nbg2, inv2, mul2(behind2, Tn2));           // dL/dalpha (finite; G = 0 below if rejected)
+                    const f2 acc_new2 = fma2(a2[r], behind2, accum_old2);
+#if EOGS_BWD_STATE_SMEM
+                    sm.state[r][lane] = make_float4(lo2(Tn2), hi2(Tn2), lo2(acc_new2), hi2(acc_new2));
+#else
+                    T2[r] = Tn2; accum2[r] = acc_new2;
+#endif
+                    const f2 u2 = mul2(Gv2[r], dLa2);
+                    const f2 ux2 = mul2(u2, dx2), uy2 = mul2(u2, bc2(dy));
+                    v2[0] = add2(v2[0], ux2);
+                    v2[1] = add2(v2[1], uy2);
+                    fma2_acc(v2[2], ux2, dx2);
+                    fma2_acc(v2[3], ux2, bc2(dy));
+                    fma2_acc(v2[4], uy2, bc2(dy));
+                    v2[5] = add2(v2[5], u2);
+                };
+#if EOGS_BWD_PAIR_ILP
+                if (live == 0xFu) {
+                    stage_b(0); stage_b(1); stage_b(2); stage_b(3);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NSTRIP; r += 2) {
+                        const uint32_t lv = (live >> r) & 3u;            // warp-uniform
+                        if (lv == 3u) { stage_b(r); stage_b(r + 1); }
+                        else if (lv == 1u) stage_b(r);
+                        else if (lv == 2u) stage_b(r + 1);
+                    }
+                }
+#else
+#pragma unroll
+                for (int r = 0; r < NSTRIP; r++) {
+                    if (!((live >> r) & 1u)) continue;               // warp-uniform
+                    stage_b(r);
+                }
+#endif
+                if (any) {
+                    const uint32_t gid = sm.rid[stage][e];
+                    float v[NV];
+#pragma unroll
+                    for (int k = 0; k < NV; k++) v[k] = lo2(v2[k]) + hi2(v2[k]);
+                    // dL_dmean2D (pixel units) = opacity * conic . (sum u dx, sum u dy); the conic sums and their -1/2
+                    // take the opacity with the slot scale
+                    const float ocx = __fmul_rn(rb.y, ra.z), ocy = __fmul_rn(rb.y, ra.w), ocz = __fmul_rn(rb.y, rb.x);
+                    const float sx = v[0], sy = v[1];
+                    v[0] = fmaf(ocx, sx, ocy * sy);
+                    v[1] = fmaf(ocz, sy, ocy * sx);
+                    const float scale_e = slot_takes_op ? slot_scale * rb.y : slot_scale;
+#if EOGS_BWD_SMEM_FLUSH
+                    __syncwarp();                                    // the previous flush's reads are done
+#pragma unroll
+                    for (int k = 0; k < NV; k++) sm.red[k][lane] = v[k];
+                    __syncwarp();
+                    if (red_h < 2) {
+                        const float4* row = reinterpret_cast<const float4*>(&sm.red[red_k][16 * red_h]);
+                        const float4 q0 = row[0], q1 = row[1], q2 = row[2], q3 = row[3];
+                        const f2 s01 = add2(add2(mk2(q0.x, q0.y), mk2(q0.z, q0.w)), add2(mk2(q1.x, q1.y), mk2(q1.z, q1.w)));
+                        const f2 s23 = add2(add2(mk2(q2.x, q2.y), mk2(q2.z, q2.w)), add2(mk2(q3.x, q3.y), mk2(q3.z, q3.w)));
+                        const f2 s = add2(s01, s23);
+                        v[0] = lo2(s) + hi2(s);
+                    }
+                    v[0] += __shfl_down_sync(FULL, v[0], NV);        // lane k < NV: its half + the half of lane k + NV
+#else
+                    warp_transpose_reduce<NV>(v, lane);
+#endif
+                    if (my_slot >= 0) atomicAdd(grad_rec + (size_t)gid * GRAD_STRIDE + my_slot, v[0] * scale_e);
+                }
+            }
+            __syncwarp();
+        }
+        cp_async_wait<0>();                    // (the last round committed an empty group)
+        __syncwarp();                          // the warp's stages and pixel constants are free for the next tile
     }
+}
+
+// Longest-first tile order for the persistent backward (one block; runs right after the forward blend).
+// work[t] = max(n_contrib) of tile t (written by blend_fwd_kernel); order = tiles with work > 0 sorted by
+// descending work (1024 buckets, order inside a bucket arbitrary); sched[0] = their number.
+__global__ void __launch_bounds__(1024)
+tile_order_kernel(uint32_t tiles, const uint32_t* __restrict__ work, uint32_t* __restrict__ order,
+                  uint32_t* __restrict__ sched)
+{
+    constexpr int NB = 1024;
+    __shared__ uint32_t s_hist[NB];
+    __shared__ uint32_t s_red[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    uint32_t mx = 0u;
+    for (uint32_t t = tid; t < tiles; t += NB) mx = max(mx, __ldg(work + t));
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) s_red[wid] = mx;
+    s_hist[tid] = 0u;
+    __syncthreads();
+    mx = s_red[lane];
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    int shift = 0;
+    while ((mx >> shift) >= (uint32_t)NB) shift++;
+    // bucket 0 = heaviest: b = NB-1 - (work >> shift); work == 0 is left out
+    for (uint32_t t = tid; t < tiles; t += NB) {
+        const uint32_t w = __ldg(work + t);
+        if (w) atomicAdd(&s_hist[NB - 1 - (w >> shift)], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of the 1024 bucket counts (one per thread)
+    const uint32_t cnt = s_hist[tid];
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    __syncthreads();
+    if (lane == 31) s_red[wid] = incl;
+    __syncthreads();
+    uint32_t wsum = s_red[lane];
+    uint32_t wincl = wsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d);
+        if (lane >= (uint32_t)d) wincl += o;
+    }
+    const uint32_t wbase = __shfl_sync(0xffffffffu, wincl - wsum, wid);
+    s_hist[tid] = wbase + incl - cnt;          // bucket start; becomes the bucket's cursor
+    if (tid == NB - 1) sched[0] = wbase + incl;
+    __syncthreads();
+    for (uint32_t t = tid; t < tiles; t += NB) {
+        const uint32_t w = __ldg(work + t);
+        if (w) order[atomicAdd(&s_hist[NB - 1 - (w >> shift)], 1u)] = t;
+    }
+}
+
+int launch_tile_order(cudaStream_t s, int W, int H, Band band, char* image, const ImageLayout& IL)
+{
+    const uint32_t tiles = (uint32_t)((W + TILE - 1) / TILE) * (uint32_t)band.rows();
+    tile_order_kernel<<<1, 1024, 0, s>>>(tiles, reinterpret_cast<const uint32_t*>(image + IL.tile_work),
+                                         reinterpret_cast<uint32_t*>(image + IL.tile_order),
+                                         reinterpret_cast<uint32_t*>(image + IL.sched));
+    EOGS_LAUNCH_CHECK("tile_order_kernel");
+    return 0;
+}
+
+static int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached = n; cached_dev = dev;
+    }
+    return cached;
 }
 
 int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
                      const GeomLayout& GL, const uint32_t* point_list, const char* image,
                      const ImageLayout& IL, const float* bg, const float* dL_dpix,
-                     const float* dL_dinvdepth, float* grad_rec)
+                     const float* dL_dinvdepth, float* grad_rec, uint32_t* queue)
 {
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = band.rows();
+#if EOGS_BWD_PERSIST
+    // persistent: as many CTAs as fit on the device at once (4 per SM), never more warps than tiles
+    const int ctas_fit = sm_count() * (16 / BWD_WARPS);
+    const int ctas_need = (tiles_x * tiles_y + BWD_WARPS - 1) / BWD_WARPS;
+    const dim3 grid(ctas_need < ctas_fit ? ctas_need : ctas_fit, 1, 1);
+#else
     const dim3 grid((tiles_x + BWD_WX - 1) / BWD_WX, (tiles_y + BWD_WY - 1) / BWD_WY, 1);
+#endif
     constexpr size_t smem = sizeof(BwdWarpSmem) * BWD_WARPS;
     cudaError_t attr_err = cudaSuccess;
     auto run = [&](auto kernel) {
@@ -341,7 +551,9 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
             reinterpret_cast<const float4*>(geom + GL.splat), reinterpret_cast<const float*>(geom + GL.cut),
             bg, W, H, tiles_x, tiles_y,
             band.row_begin, band.height(H), reinterpret_cast<const float*>(image + IL.final_T),
-            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), dL_dpix, dL_dinvdepth, grad_rec);
+            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), dL_dpix, dL_dinvdepth, grad_rec,
+            reinterpret_cast<const uint32_t*>(image + IL.tile_order),
+            reinterpret_cast<const uint32_t*>(image + IL.sched), queue);
     };
     if (channels == 5) run(blend_bwd_kernel<5>);
     else if (channels == 3) run(blend_bwd_kernel<3>);

@@ -1,31 +1,20 @@
-// Staging machinery shared by the forward and backward blend kernels.
+// Pieces shared by the forward and backward blend kernels: the exact patch-culling test, the warp
+// reduction of the backward's per-Gaussian terms, and the approximate MUFU wrappers.
 //
-// A 256-thread CTA owns a 16x16 tile; warp w owns the 8x4 pixel patch
-//     x in [tile_x + 8*(w&1), +7],  y in [tile_y + 4*(w>>1), +3]          (tile_pixel, common.cuh)
-// Per batch of 256 list entries, thread t fetches entry t's packed record and decides, once, which
-// of the 8 warp patches the Gaussian can reach with alpha >= 1/255 (tile_may_contribute on the tile,
-// then on each patch): an 8-bit mask.  The record is stored at slot t of the batch's shared-memory
-// stage and t is appended — in list order — to the private entry list of every warp whose bit is set
-// (warp ballots; per-(consumer warp, staging warp) segments so no cross-warp prefix sum and no extra
-// barrier is needed).  The consumer warps then iterate only over entries that can touch their own
-// 32 pixels.  The reference evaluates every entry of the tile list in every one of the 256 threads
-// (forward.cu:356-372, backward.cu:551-577).  Culling is exact and conservative: it only removes
-// (pixel, Gaussian) pairs that the per-pixel test would reject, so images, n_contrib and gradients
-// are unchanged; the tile lists themselves stay the reference's.
+// A 16x16 tile is cut into eight 8x4 pixel PATCHES (patch p: x in [8*(p&1), +7], y in [4*(p>>1), +3]).
+// The thread that stages a list entry decides ONCE which patches the Gaussian can reach with
+// alpha >= 1/255 (patch_mask below): the forward kernel (128 threads, warp = 8x8 region = two patches)
+// appends the entry only to the regions it reaches, the backward kernel (one warp per tile, lane = one
+// pixel of every patch) skips entries and half tiles nobody reaches.  The reference evaluates every
+// entry of the tile list in every one of the 256 threads (forward.cu:356-372, backward.cu:551-577).
+// Culling is exact and conservative: it only removes (pixel, Gaussian) pairs that the per-pixel test
+// would reject, so images, n_contrib and gradients are unchanged; the tile lists stay the reference's.
 #pragma once
 #include "common.cuh"
 
 namespace eogs {
 
-constexpr int BLEND_THREADS = TILE_PIXELS;          // 256
-constexpr int BLEND_WARPS = BLEND_THREADS / 32;     // 8
 constexpr int PATCH_W = 8, PATCH_H = 4;
-
-struct BlendStage {
-    float4 rec[REC_F4][BLEND_THREADS];                       // packed records, slot = position in batch
-    uint8_t list[BLEND_WARPS][BLEND_WARPS][32];              // [consumer warp][staging warp][rank] -> slot
-    uint8_t cnt[BLEND_WARPS][BLEND_WARPS];                   // [consumer warp][staging warp]
-};
 
 // 8-bit mask of the warp patches this Gaussian may contribute to (bit w = patch of warp w).
 //
@@ -81,41 +70,6 @@ __device__ __forceinline__ uint32_t patch_mask(const float4& r0, const float4& r
     return m;
 }
 
-// Warp-collective: store this thread's record at slot tid and append tid to the consumer lists.
-__device__ __forceinline__ void stage_entry(BlendStage& st, uint32_t tid, uint32_t mask,
-                                            const float4& r0, const float4& r1, const float4& r2) {
-    const uint32_t lane = tid & 31u, swarp = tid >> 5;
-    if (mask) {
-        st.rec[0][tid] = r0;
-        st.rec[1][tid] = r1;
-        st.rec[2][tid] = r2;
-    }
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int w = 0; w < BLEND_WARPS; w++) {
-        const bool mine = (mask >> w) & 1u;
-        const uint32_t ballot = __ballot_sync(0xffffffffu, mine);
-        if (mine) st.list[w][swarp][__popc(ballot & lt)] = (uint8_t)tid;
-        if (lane == (uint32_t)w) st.cnt[w][swarp] = (uint8_t)__popc(ballot);
-    }
-}
-
-__device__ __forceinline__ void fetch_record(const float4* __restrict__ splat, uint32_t id,
-                                             float4& r0, float4& r1, float4& r2) {
-    const float4* src = splat + (size_t)id * REC_F4;
-    r0 = __ldg(src); r1 = __ldg(src + 1); r2 = __ldg(src + 2);
-}
-
-// The reference's per-pair exponent, in the op order of its sm_100a SASS (forward.cu:361-365):
-// power = -0.5f * (con.x*dx*dx + con.z*dy*dy) - con.y*dx*dy
-__device__ __forceinline__ float pair_power(const float4& ra, const float4& rb, float pixfx, float pixfy,
-                                            float& dx, float& dy) {
-    dx = __fsub_rn(ra.x, pixfx);
-    dy = __fsub_rn(ra.y, pixfy);
-    const float quad = __fmaf_rn(dx, __fmul_rn(ra.z, dx), __fmul_rn(__fmul_rn(rb.x, dy), dy));
-    return __fmaf_rn(quad, -0.5f, -__fmul_rn(__fmul_rn(ra.w, dx), dy));
-}
-
 // ---- warp reduction of the backward's per-pair terms ------------------------------------------
 // Transposing butterfly level: N live values -> ceil(N/2), partner = lane ^ (1 << BIT).
 template <int N, int BIT>
@@ -168,13 +122,6 @@ __device__ __forceinline__ float fast_rcp(float x) {      // x in [0.01, 1]: no 
 __device__ __forceinline__ float ex2_approx(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// exp(x) for x <= 0 through ex2.approx (relative error ~2^-22); backward only.
-__device__ __forceinline__ float fast_exp(float x) {
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
     return r;
 }
 

@@ -128,6 +128,7 @@ EOGS_API size_t eogs_image_bytes_band(int W, int H, int row_begin, int row_end) 
     return image_layout(W, H, b).total;
 }
 EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t I) { return binning_layout(W, H, I).total; }
+EOGS_API size_t eogs_grad_scratch_floats(int P) { return (size_t)(P > 0 ? P : 0) * GRAD_STRIDE + GRAD_TAIL; }
 
 static int forward_geometry_impl(eogs_stream_t stream, int P, int W, int H, int channels,
                           int row_begin, int row_end, bool raw_params, const float* alt_affine,
@@ -318,13 +319,13 @@ static int backward_impl(eogs_stream_t stream, int P, int W, int H, int channels
     if (!cov3D_precomp && (!scales || !rotations)) { set_error("need scales+rotations or cov3D_precomp"); return -4; }
     const GeomLayout GL = geom_layout(P);
     const ImageLayout IL = image_layout(W, H, band);
-    EOGS_CUDA(cudaMemsetAsync(grad_scratch, 0, (size_t)P * GRAD_STRIDE * sizeof(float), s));
+    EOGS_CUDA(cudaMemsetAsync(grad_scratch, 0, ((size_t)P * GRAD_STRIDE + GRAD_TAIL) * sizeof(float), s));
     prof_mark(s, ST_BWD_ZERO);
     if (num_instances > 0) {
         if (!point_list) { set_error("null point_list"); return -4; }
         if (int rc = launch_blend_bwd(s, W, H, band, channels, static_cast<const char*>(geom), GL, point_list,
                                       static_cast<const char*>(image), IL, bg, dL_dpix, dL_dinvdepth,
-                                      grad_scratch)) return rc;
+                                      grad_scratch, reinterpret_cast<uint32_t*>(grad_scratch + (size_t)P * GRAD_STRIDE))) return rc;
     }
     prof_mark(s, ST_BLEND_BWD);
     const int rc_pre = launch_preprocess_bwd(s, P, W, H, channels, raw_params, alt_affine, alt_sums, means3D, scales, rotations, cov3D_precomp, opacities,

@@ -12,6 +12,7 @@ constexpr int TILE = EOGS_TILE;          // 16x16 pixel tiles (key parity with D
 constexpr int TILE_PIXELS = TILE * TILE;
 constexpr int REC_F4 = 3;                // float4s per packed splat record (48 bytes)
 constexpr int GRAD_STRIDE = 16;          // floats per Gaussian in the blend-backward gradient record
+constexpr int GRAD_TAIL = 16;            // floats after the P records of grad_scratch: [0] = the backward's tile-queue counter
 
 // ---- packed per-Gaussian splat record (what the blend kernels gather) -----------------
 //   rec[0] = { mean2D.x, mean2D.y, conic.x, conic.y }
@@ -43,6 +44,9 @@ struct ImageLayout {
     size_t final_T;      // float[W*band_height]
     size_t n_contrib;    // u32[W*band_height]
     size_t ranges;       // uint2[band tiles]
+    size_t tile_work;    // u32[band tiles]   max(n_contrib) of the tile (blend forward) = the backward's replay length
+    size_t tile_order;   // u32[band tiles]   tiles with work > 0, longest first (the persistent backward's queue)
+    size_t sched;        // u32[4]            [0] = number of queued tiles
     size_t total;
 };
 
@@ -123,7 +127,9 @@ int launch_blend_fwd(cudaStream_t s, int W, int H, Band band, int channels, cons
 int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
                      const GeomLayout& GL, const uint32_t* point_list, const char* image,
                      const ImageLayout& IL, const float* bg, const float* dL_dpix,
-                     const float* dL_dinvdepth, float* grad_rec);
+                     const float* dL_dinvdepth, float* grad_rec, uint32_t* queue);
+
+int launch_tile_order(cudaStream_t s, int W, int H, Band band, char* image, const ImageLayout& IL);
 
 int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels, bool raw_params,
                           const float* alt_affine, float* alt_sums,
@@ -138,47 +144,6 @@ int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels, boo
 // ---- device helpers ---------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
-
-// Pixel owned by a thread of a 256-thread tile block.  A warp covers an 8x4 pixel patch
-// (not the reference's 16x2 strip): a more compact footprint makes whole-warp skips of
-// non-overlapping Gaussians and warp-coherent early termination more likely.  The mapping
-// is internal — per-pixel results do not depend on it.
-__device__ __forceinline__ void tile_pixel(uint32_t tid, uint32_t& lx, uint32_t& ly) {
-    const uint32_t lane = tid & 31u, warp = tid >> 5;
-    lx = ((warp & 1u) << 3) | (lane & 7u);
-    ly = ((warp >> 1) << 2) | (lane >> 3);
-}
-
-// Exact, conservative tile culling.  Can the Gaussian (mean m, conic (A, B, C), opacity op) reach
-// alpha >= 1/255 at ANY point of the pixel rectangle [x0,x1] x [y0,y1]?  alpha = op * exp(-q/2) with
-// q(d) = A dx^2 + 2 B dx dy + C dy^2 positive definite, so the question is whether
-// min_rect q <= 2 ln(255 op).  The minimiser over the rectangle is the centre when it lies inside,
-// otherwise it lies on an edge facing the centre (at most two), where q restricted to the edge is
-// a 1-D parabola whose clamped minimum is closed-form.  The reference has every pixel of the tile
-// evaluate and reject such Gaussians one by one (forward.cu:361-372); skipping them for the whole
-// tile cannot change any pixel.  A margin of 0.05 on the exponent covers the rounding of this
-// bound versus the per-pixel expression; NaNs compare false and keep the entry.
-__device__ __forceinline__ bool tile_may_contribute(float mx, float my, float A, float B, float C, float op,
-                                                    float x0, float y0, float x1, float y1) {
-    const float ex = fminf(fmaxf(mx, x0), x1), ey = fminf(fmaxf(my, y0), y1);
-    const float dxe = ex - mx, dye = ey - my;          // zero when the centre is inside in that dimension
-    float qmin = 0.f;
-    if (dxe != 0.f || dye != 0.f) {
-        qmin = 3.0e38f;
-        if (dxe != 0.f) {                               // facing vertical edge x = ex
-            const float ys = fminf(fmaxf(my - __fdividef(B * dxe, C), y0), y1);
-            const float dy = ys - my;
-            qmin = fminf(qmin, A * dxe * dxe + 2.f * B * dxe * dy + C * dy * dy);
-        }
-        if (dye != 0.f) {                               // facing horizontal edge y = ey
-            const float xs = fminf(fmaxf(mx - __fdividef(B * dye, A), x0), x1);
-            const float dx = xs - mx;
-            qmin = fminf(qmin, A * dx * dx + 2.f * B * dx * dye + C * dye * dye);
-        }
-    }
-    const float thr = -__logf(255.f * op);             // alpha >= 1/255  <=>  power >= thr
-    return !(-0.5f * qmin + 0.05f < thr);
-}
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);

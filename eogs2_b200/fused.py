@@ -120,7 +120,7 @@ def backward_params_raw(state: ForwardState, bg, xyz, opacity_logits, log_scales
             raise RuntimeError("grad_out_color does not match the rendered image")
         if dL_dinvdepth is not None:
             dL_dinvdepth = _f32c(dL_dinvdepth, "grad_out_depth", dev)
-        grad_scratch = torch.empty(P * 16, **opts)
+        grad_scratch = torch.empty(lib.eogs_grad_scratch_floats(P), **opts)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _cabi.check(lib.eogs_backward_params_band(
             stream, P, W, H, rb, re, state.num_rendered, _ptr(xyz), _ptr(log_scales), _ptr(raw_rotations),

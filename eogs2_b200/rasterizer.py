@@ -275,7 +275,7 @@ def rasterize_backward_raw(state: ForwardState, bg, means3D, colors, opacities, 
             dL_dinvdepth = _f32c(dL_dinvdepth, "grad_out_depth", dev)
             if dL_dinvdepth.numel() != state.band_height * W:
                 raise RuntimeError("grad_out_depth does not match the rendered band")
-        grad_scratch = torch.empty(P * 16, **opts)
+        grad_scratch = torch.empty(lib.eogs_grad_scratch_floats(P), **opts)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _cabi.check(lib.eogs_backward_band(
             stream, P, W, H, ch, rb, re, state.num_rendered,

@@ -51,7 +51,7 @@ extern "C" {
 #define EOGS_API
 #endif
 
-#define EOGS_ABI_VERSION 5
+#define EOGS_ABI_VERSION 6
 #define EOGS_TILE 16            /* BLOCK_X = BLOCK_Y = 16, DGR/cuda_rasterizer/config.h:15-16 */
 #define EOGS_MAX_CHANNELS 5     /* NUM_CHANNELS 5,        DGR/cuda_rasterizer/config.h:14    */
 
@@ -87,6 +87,11 @@ EOGS_API size_t eogs_image_bytes(int W, int H);
  * Gaussian list, which is the separate `point_list` argument (4*I bytes) because it is
  * the only part backward needs. */
 EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t num_instances);
+/* Floats of backward scratch for P Gaussians: one 16-float gradient record per Gaussian (what the
+ * reference keeps in dL_dconic / dL_dmeans2D / dL_dopacity / dL_dcolors between its two backward
+ * kernels, rasterize_points.cu:163-183) + a small tail holding the tile-queue counter of the blend
+ * backward.  Zeroed by every backward call. */
+EOGS_API size_t eogs_grad_scratch_floats(int P);
 
 /* ---- forward, stage 1: per-Gaussian geometry -------------------------------------- */
 /* Affine projection, 3D->2D covariance, conic, radius, tile rect, depth = 200 - altitude,
@@ -141,7 +146,7 @@ EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, i
 /* ---- backward ----------------------------------------------------------------------- */
 /* Blend backward + preprocess backward + camera-gradient reductions.
  *   dL_dpix [channels,H,W] dev; dL_dinvdepth [H,W] dev or NULL
- *   grad_scratch dev: 16*P floats, zeroed by this call
+ *   grad_scratch dev: eogs_grad_scratch_floats(P) floats (16 per Gaussian + 16), zeroed by this call
  * outputs (all dev, all written by this call; culled Gaussians get zeros):
  *   dL_dmeans2D [P,3] (z = 0)   dL_dcolors [P,channels]   dL_dopacity [P]
  *   dL_dmeans3D [P,3]           dL_dcov3D [P,6] or NULL    dL_dscales [P,3] or NULL

@@ -19,25 +19,29 @@ from pathlib import Path
 import torch
 
 LIB_PATH = Path(__file__).resolve().parent / "_ref" / "libeogs_ref.so"
+# The same sources with the one-line `dL_dT[6*idx+k]` stride fix of backward.cu:320-325 (oracle/ref_build/Makefile):
+# the race-free reference value of the camera-covariance term of grad_viewmatrix.
+STRIDEFIX_PATH = LIB_PATH.with_name("libeogs_ref_stridefix.so")
 NUM_CHANNELS = 5
 _ALLOC_T = C.CFUNCTYPE(C.c_void_p, C.c_int, C.c_size_t)
-_lib = None
+_libs: dict = {}
 
 
-def available() -> bool:
-    return LIB_PATH.exists()
+def available(stridefix: bool = False) -> bool:
+    return (STRIDEFIX_PATH if stridefix else LIB_PATH).exists()
 
 
-def load() -> C.CDLL:
-    global _lib
-    if _lib is None:
-        if not LIB_PATH.exists():
-            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle/ref_build` where /root/reference exists")
-        lib = C.CDLL(os.fspath(LIB_PATH))
+def load(stridefix: bool = False) -> C.CDLL:
+    path = STRIDEFIX_PATH if stridefix else LIB_PATH
+    lib = _libs.get(path)
+    if lib is None:
+        if not path.exists():
+            raise RuntimeError(f"{path} missing: run `make -C oracle/ref_build` where /root/reference exists")
+        lib = C.CDLL(os.fspath(path))
         lib.eogs_ref_forward.restype = C.c_int
         lib.eogs_ref_backward.restype = C.c_int
-        _lib = lib
-    return _lib
+        _libs[path] = lib
+    return lib
 
 
 def _p(t):
@@ -87,9 +91,10 @@ def forward(bg, means3D, colors, opacities, scales, rotations, scale_modifier, c
 
 def backward(st: RefState, bg, means3D, colors, opacities, scales, rotations, scale_modifier,
              cov3D_precomp, viewmatrix, projmatrix, tanfovx, tanfovy, dL_dcolor, dL_dinvdepth, campos,
-             antialiasing=False, debug=False) -> dict:
-    """_C.rasterize_gaussians_backward (DGR/rasterize_points.cu:126-224)."""
-    lib = load()
+             antialiasing=False, debug=False, stridefix=False) -> dict:
+    """_C.rasterize_gaussians_backward (DGR/rasterize_points.cu:126-224).  stridefix=True runs the backward of
+    the stride-fixed build on the same forward state (identical layouts; only the dL_dT store differs)."""
+    lib = load(stridefix)
     dev = means3D.device
     P, H, W = st.P, st.H, st.W
     z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)

@@ -1,0 +1,59 @@
+"""Shared comparison helpers of the GPU parity tests (test infrastructure).
+
+Gradient bar ("<= 1e-3 relative"), applied PER GAUSSIAN and per element instead of as one
+L2 ratio over all P (which hides single-Gaussian outliers — exactly the failure an alpha-threshold flip produces):
+
+    |a[p, k] - b[p, k]|  <=  rtol * max_k |b[p, k]|  +  atol_frac * max |b|
+
+The first term is relative to the Gaussian's own gradient vector (for one-component tensors: to the element itself),
+the second is the noise floor of float accumulation: both implementations sum ~10^2..10^4 signed terms per Gaussian in
+an order that atomics make run-dependent, so an element that is a near-complete cancellation carries an absolute error
+of a few ulps of the terms.  Measured (tools/grad_outliers.py, profiles/r2c_grad_outliers.json): against the float64
+C oracle the worst per-Gaussian relative error is 5e-4 and the absolute floor 1e-7 x max|b|; the compiled reference
+differs from ITSELF between two runs by up to 4e-2 per Gaussian on dL_dscales at 1 M Gaussians (ill-conditioned
+covariance chain), which is why comparisons against it are made relative to its own run-to-run noise
+(`violations` + `assert_no_worse_than_rerun`)."""
+import numpy as np
+
+
+def _rows(x, P=None):
+    x = np.asarray(x.detach().cpu().numpy() if hasattr(x, "detach") else x, np.float64)
+    return x.reshape(x.shape[0] if P is None else P, -1)
+
+
+def violations(a, b, rtol=1e-3, atol_frac=1e-6):
+    """Per-element excess over the bar, reduced per Gaussian.  Returns (rows violating, worst excess / max|b|, rows)."""
+    a, b = _rows(a), _rows(b)
+    absmax = np.abs(b).max() if b.size else 0.0
+    bar = rtol * np.abs(b).max(1, keepdims=True) + atol_frac * absmax
+    excess = (np.abs(a - b) - bar).max(1) if b.size else np.zeros(0)
+    bad = np.nonzero(excess > 0)[0]
+    worst = float(excess.max() / absmax) if (b.size and absmax > 0) else 0.0
+    return len(bad), max(worst, 0.0), bad
+
+
+def assert_grad_close(a, b, what, rtol=1e-3, atol_frac=1e-6, allow_rows=0):
+    """Every Gaussian within the bar, except `allow_rows` (Gaussians that own a pixel whose accept decision flipped
+    between two exp implementations; 0 when both sides use the same one)."""
+    n, worst, bad = violations(a, b, rtol, atol_frac)
+    assert n <= allow_rows, f"{what}: {n} Gaussians exceed the per-element bar (allowed {allow_rows}); worst excess " \
+                            f"{worst:.2e} x max|ref|; first rows {bad[:8].tolist()}"
+
+
+def assert_no_worse_than_rerun(ours, ref, ref_rerun, what, rtol=1e-3, atol_frac=1e-6, factor=3.0, slack_rows=2):
+    """Against a reference whose own atomics make it non-deterministic: our violations of the bar must be explained
+    by the reference's run-to-run noise — no more violating Gaussians than `factor` x (what the reference shows against
+    itself) + slack, and no worse excess."""
+    n, worst, bad = violations(ours, ref, rtol, atol_frac)
+    n0, worst0, _ = violations(ref_rerun, ref, rtol, atol_frac)
+    # 1e-4 x max|ref|: the absolute excess seen between two runs of the reference at 1 M Gaussians (dL_dscales 1.4e-4,
+    # dL_drotations 2e-5 .. 5e-5; profiles/r2c_grad_outliers.json) — the statistic of a handful of outliers is itself noisy
+    assert n <= factor * n0 + slack_rows and worst <= factor * worst0 + 1e-4, \
+        f"{what}: {n} Gaussians over the bar (reference vs its own rerun: {n0}), worst excess {worst:.2e} vs {worst0:.2e}; " \
+        f"rows {bad[:8].tolist()}"
+
+
+def assert_analytic_zero(t, scale, what, frac=1e-6):
+    """A gradient that is analytically zero (dL/dquaternion of an isotropic Gaussian): only rounding noise may remain."""
+    m = float(np.abs(_rows(t)).max()) if t.numel() else 0.0
+    assert m <= frac * scale, f"{what}: |value| up to {m:.2e}, expected rounding noise below {frac * scale:.2e}"

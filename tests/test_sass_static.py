@@ -54,7 +54,9 @@ def test_blend_kernels_use_packed_fp32x2_and_async_staging(kernels):
     for c in find(kernels, "blend_bwd_kernelILi5"):
         assert c["FFMA2"] >= 60 and c["FMUL2"] >= 30, c
         assert c["LDGSTS"] >= 4
-        assert c["REDG"] == 1 and c["ATOMG"] == 0               # ONE red.global per (tile, Gaussian) flush, no returning atomics
+        # ONE red.global per (tile, Gaussian) flush; the only returning atomic is the tile-queue pull (one per tile)
+        assert c["REDG"] == 1 and c["ATOMG"] == 1
+        assert c["REDUX"] >= 1                                  # per-entry strip liveness in one warp reduction
         assert c["SHFL"] <= 16                                  # transposing butterfly: 13 shuffles for 11 values
         assert c["BAR"] == 0                                    # warp-synchronous: no block barrier at all
 
