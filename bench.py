@@ -46,7 +46,7 @@ sys.path.insert(0, str(ROOT))
 P_GAUSS = 1_000_000
 IMG = 2048
 SEED = 1337
-STAGES = ["", "preprocess", "depth_sort", "scan", "emit", "tile_sort", "ranges", "blend_fwd",
+STAGES = ["", "preprocess", "depth_sort", "bin_rows", "bin_count", "bin_scatter", "blend_fwd",
           "bwd_zero", "blend_bwd", "preprocess_bwd"]
 
 

@@ -1,20 +1,29 @@
-// Binning: depth order of Gaussians, instance emission, tile sort, tile ranges.
+// Binning: depth order of Gaussians, then the per-tile depth-sorted Gaussian lists and the tile ranges.
 // Replaces cub InclusiveSum + duplicateWithKeys + 64-bit cub SortPairs + identifyTileRanges
 // (DGR/cuda_rasterizer/rasterizer_impl.cu:70-138, 280-321).
 //
-// The reference sorts I instances on a 64-bit (tile | depth bits) key: ceil((32+bit)/8) = 6-7
-// radix passes over 12-byte pairs.  The order it produces is fully determined — (tile, depth
-// bits, Gaussian id) because the LSD sort is stable and emission is id-ascending — so we get
-// the identical list with far less traffic:
-//   1. sort the P Gaussians once by (depth bits, id)          (P << I, 32-bit keys)
-//   2. emit instances in that order                            (balanced, coalesced)
-//   3. stable-sort instances by tile id only                  (ceil(bit/8) = 2-3 passes over
-//                                                              8-byte pairs)
-// Algorithmic bytes per instance: 8 emitted + 16*passes*... see DESIGN.md.
+// The reference materialises I = sum(tiles touched) (key, value) instances and radix-sorts them on a 64-bit
+// (tile | depth bits) key: ceil((32+bit)/8) = 6-7 passes over 12-byte pairs.  The order it produces is fully
+// determined — (tile, depth bits, Gaussian id), because the LSD sort is stable and emission is id-ascending — so the
+// identical list can be built without ever sorting instances:
+//   1. sort the P Gaussians once by (depth bits, id)                    (P << I; 32-bit keys, library radix sort)
+//   2. a tile's list is "the Gaussians whose tile rectangle covers it, in that order".  A rectangle is a set of ROW
+//      RUNS [x0, x1) x {y}; the lists are built by two stable counting passes that only ever touch runs and ids:
+//        rows:     each chunk of 1024 depth-ordered Gaussians counts its runs per tile row (difference array +
+//                  prefix sum in shared memory), a column scan over chunks gives every (chunk, row) its base, and
+//                  the chunk writes its runs {id, x0, x1} into the row's run list IN DEPTH ORDER — the rank of a
+//                  Gaussian inside (chunk, row) is a popcount over a 1024-bit occupancy bitmap of that row;
+//        columns:  the same three steps on sub-chunks of 1024 runs of one row, over tile columns: counts per
+//                  (sub-chunk, tile), scan over sub-chunks (whose per-tile totals ARE the tile list lengths, i.e. the
+//                  reference's ranges after one scan over tiles), and the scatter of the ids into point_list.
+// No instance keys exist at any point; eogs_export_state rebuilds the reference's 64-bit keys from ranges, point_list
+// and the depths for the parity tests, and the lists / ranges are bit-identical to the reference's.
+//
+// Algorithmic bytes: 12 B/Gaussian read twice, 8 B/run written once and read twice, 4 B/instance written once —
+// about 11 B/instance on the bench scene (3.9 runs of 4 tiles per Gaussian) against 32 B/instance for emission +
+// a 16-bit two-pass radix sort of the instances (the previous version) and 176-200 B/instance in the reference.
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/transform_iterator.h>
 
 namespace eogs {
 
@@ -34,7 +43,6 @@ GeomLayout geom_layout(int P) {
     L.key_out = take(n * 4);
     L.id_in = take(n * 4);
     L.order = take(n * 4);
-    L.offsets = take(n * 4);
     L.temp_bytes = sort_temp_bound(n);
     L.temp = take(L.temp_bytes);
     L.total = off;
@@ -68,27 +76,33 @@ ImageLayout image_layout(int W, int H, Band band) {
     return L;
 }
 
+constexpr int BIN_CH = 1024;                 // Gaussians per row chunk = runs per column sub-chunk = bits per bitmap row
+constexpr int BIN_WORDS = BIN_CH / 32;
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_IPT = BIN_CH / BIN_THREADS; // items per thread
+constexpr int BIN_WIN = 1024;                // tile rows (columns) per shared-memory window
+constexpr int BIN_ROW = BIN_WORDS + 1;       // bitmap row stride in words: rows land in distinct banks
+
 BinningLayout binning_layout(int W, int H, uint32_t I) {
-    (void)W; (void)H;
     BinningLayout L;
     const size_t n = (size_t)(I > 0 ? I : 1);
+    const size_t gx = (size_t)((W + TILE - 1) / TILE), gy = (size_t)((H + TILE - 1) / TILE);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    L.key_in = take(n * 4);
-    L.key_out = take(n * 4);
-    L.val_in = take(n * 4);
-    L.temp_bytes = sort_temp_bound(n);
-    L.temp = take(L.temp_bytes);
+    // every visible Gaussian owns at least one instance and every run at least one: I bounds both counts
+    L.chunk_cap = n / BIN_CH + 1;
+    L.sub_cap = n / BIN_CH + gy + 1;
+    L.row_count = take(L.chunk_cap * gy * 4);
+    L.row_total = take((gy + 1) * 4);
+    L.row_start = take((gy + 1) * 4);
+    L.sub_first = take((gy + 1) * 4);
+    L.runs = take(n * 8);
+    L.col_count = take(L.sub_cap * gx * 4);
     L.total = off;
     return L;
 }
 
-// ---- stage 1b: depth order + offsets -------------------------------------------------------
-struct GatherTiles {
-    const uint32_t* tiles;
-    __host__ __device__ uint32_t operator()(uint32_t g) const { return tiles[g]; }
-};
-
+// ---- stage 1b: depth order -------------------------------------------------------
 int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
                        eogs_forward_info* info_dev)
 {
@@ -96,8 +110,6 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
     uint32_t* key_out = reinterpret_cast<uint32_t*>(geom + L.key_out);
     uint32_t* id_in = reinterpret_cast<uint32_t*>(geom + L.id_in);
     uint32_t* order = reinterpret_cast<uint32_t*>(geom + L.order);
-    uint32_t* offsets = reinterpret_cast<uint32_t*>(geom + L.offsets);
-    const uint32_t* tiles = reinterpret_cast<const uint32_t*>(geom + L.tiles);
     void* temp = geom + L.temp;
 
     // (depth bits, id): keys are non-negative floats, so their bit patterns order like the
@@ -113,172 +125,376 @@ int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
     if (vals.Current() != order)
         EOGS_CUDA(cudaMemcpyAsync(order, vals.Current(), (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
 
+    (void)info_dev;      // num_instances was already published by the preprocess kernel
     prof_mark(s, ST_DEPTH_SORT);
-    auto in = thrust::make_transform_iterator(static_cast<const uint32_t*>(order), GatherTiles{tiles});
-    need = 0;
-    EOGS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, need, in, offsets, P, s));
-    if (need > L.temp_bytes) { set_error("scan temp %zu > %zu", need, L.temp_bytes); return -3; }
-    need = L.temp_bytes;
-    EOGS_CUDA(cub::DeviceScan::InclusiveSum(temp, need, in, offsets, P, s));
-
-    (void)info_dev;      // num_instances = offsets[P-1] was already published by the preprocess kernel
-    prof_mark(s, ST_SCAN);
     return 0;
 }
 
-// ---- stage 2a: instance emission -----------------------------------------------------------
-// One block per 256 depth-ordered Gaussians.  The block's instances form one contiguous output
-// range; thread t writes outputs t, t+256, ... and finds the owning Gaussian by binary search in
-// the block's 256 relative offsets (shared memory).  Balanced regardless of footprint size, and
-// both stores are fully coalesced — the reference loops serially per Gaussian
-// (rasterizer_impl.cu:96-108).
-constexpr int EMIT_THREADS = 256;
+// ---- stage 2: tile lists ------------------------------------------------------------------------
+// Shared pieces of the two counting passes.  An ITEM is a half-open interval [lo, hi) of bins plus a payload:
+//   rows pass:     item = depth-ordered Gaussian, bins = tile rows of the band,    payload = {id, x0 | x1 << 16}
+//   columns pass:  item = run of one tile row,    bins = tile columns,             payload = id
 
-template <typename KeyT>
-__global__ void __launch_bounds__(EMIT_THREADS)
-emit_instances_kernel(int P, int grid_x, uint32_t band_y0, const uint32_t* __restrict__ order,
-                      const uint32_t* __restrict__ offsets, const uint2* __restrict__ rect,
-                      KeyT* __restrict__ tile_keys, uint32_t* __restrict__ ids)
+// exclusive scan of one value per thread over a block of NT threads; returns the exclusive prefix, total in `total`
+template <int NT>
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t w = lane < NT / 32 ? s_warp[lane] : 0u, wincl = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, wincl, d);
+        if (lane >= (uint32_t)d) wincl += o;
+    }
+    total = __shfl_sync(0xffffffffu, wincl, NT / 32 - 1);
+    const uint32_t wbase = __shfl_sync(0xffffffffu, wincl - w, wid);
+    __syncthreads();                                   // s_warp may be reused by the caller
+    return wbase + incl - v;
+}
+
+// Which column sub-chunk is block `s`: row y with sub_first[y] <= s < sub_first[y + 1], runs [beg, end) of that row.
+__device__ __forceinline__ bool locate_sub(uint32_t s, int gy, const uint32_t* __restrict__ sub_first,
+                                           const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ row_total,
+                                           int& y, uint32_t& beg, uint32_t& end) {
+    if (s >= __ldg(sub_first + gy)) return false;
+    int lo = 0, hi = gy;                               // largest y with sub_first[y] <= s
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(sub_first + mid) <= s) lo = mid; else hi = mid;
+    }
+    y = lo;
+    const uint32_t rs = __ldg(row_start + y);
+    beg = rs + (s - __ldg(sub_first + y)) * BIN_CH;
+    end = min(beg + BIN_CH, rs + __ldg(row_total + y));
+    return true;
+}
+
+// Counting: out[bin] = number of the block's items whose interval covers bin (difference array + prefix sum).
+__device__ __forceinline__ void count_cover(const int (&lo)[BIN_IPT], const int (&hi)[BIN_IPT], int nbins,
+                                            uint32_t* __restrict__ out, int* s_diff, uint32_t* s_warp) {
+    for (int w0 = 0; w0 < nbins; w0 += BIN_WIN) {
+        const int wn = min(BIN_WIN, nbins - w0);
+        for (int i = threadIdx.x; i <= BIN_WIN; i += BIN_THREADS) s_diff[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BIN_IPT; k++) {
+            const int a = max(lo[k], w0) - w0, b = min(hi[k], w0 + wn) - w0;
+            if (a < b) { atomicAdd(&s_diff[a], 1); atomicAdd(&s_diff[b], -1); }
+        }
+        __syncthreads();
+        // inclusive prefix over the window: thread t owns entries 4t .. 4t+3
+        int d[BIN_IPT];
+        uint32_t sum = 0u;
+#pragma unroll
+        for (int k = 0; k < BIN_IPT; k++) { d[k] = s_diff[BIN_IPT * threadIdx.x + k]; sum += (uint32_t)d[k]; }
+        uint32_t tot;
+        uint32_t run = block_scan_excl<BIN_THREADS>(sum, s_warp, tot);
+#pragma unroll
+        for (int k = 0; k < BIN_IPT; k++) {
+            run += (uint32_t)d[k];
+            const int i = BIN_IPT * (int)threadIdx.x + k;
+            if (i < wn) out[w0 + i] = run;
+        }
+        __syncthreads();
+    }
+}
+
+// Scatter: the block's items, in order, to out[base(bin) + rank]; rank = number of earlier items of the block that
+// cover the same bin = popcount over the bin's occupancy bitmap (one bit per item).
+template <typename Payload, typename BaseFn>
+__device__ __forceinline__ void scatter_cover(int n_local, const uint32_t* s_lohi, const Payload* s_pay, int nbins,
+                                              uint32_t* s_bits, Payload* __restrict__ out, BaseFn base_of) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (int w0 = 0; w0 < nbins; w0 += BIN_WIN) {
+        const int wn = min(BIN_WIN, nbins - w0);
+        for (int i = threadIdx.x; i < wn * BIN_ROW; i += BIN_THREADS) s_bits[i] = 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BIN_IPT; k++) {
+            const int j = (int)threadIdx.x + k * BIN_THREADS;
+            if (j >= n_local) continue;
+            const uint32_t lh = s_lohi[j];
+            const int a = max((int)(lh & 0xFFFFu), w0), b = min((int)(lh >> 16), w0 + wn);
+            for (int bin = a; bin < b; bin++) atomicOr(&s_bits[(bin - w0) * BIN_ROW + (j >> 5)], 1u << (j & 31));
+        }
+        __syncthreads();
+        for (int r = (int)warp; r < wn; r += BIN_THREADS / 32) {
+            uint32_t bits = s_bits[r * BIN_ROW + lane];
+            const uint32_t c = (uint32_t)__popc(bits);
+            uint32_t incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (uint32_t)d) incl += o;
+            }
+            if (__shfl_sync(0xffffffffu, incl, 31) == 0u) continue;       // nobody covers this bin
+            uint32_t pos = base_of(w0 + r) + incl - c;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                out[pos++] = s_pay[lane * 32 + b];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// rows, step 1: per (chunk of 1024 depth-ordered Gaussians, tile row) the number of runs
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_count_rows_kernel(int n_items, int gy, int band_y0, const uint32_t* __restrict__ order,
+                      const uint2* __restrict__ rect, uint32_t* __restrict__ row_count)
 {
-    __shared__ uint32_t s_end[EMIT_THREADS];
-    __shared__ uint32_t s_id[EMIT_THREADS];
-    __shared__ uint2 s_rect[EMIT_THREADS];
+    __shared__ int s_diff[BIN_WIN + 1];
+    __shared__ uint32_t s_warp[32];
+    int lo[BIN_IPT], hi[BIN_IPT];
+#pragma unroll
+    for (int k = 0; k < BIN_IPT; k++) {
+        const int j = (int)blockIdx.x * BIN_CH + (int)threadIdx.x + k * BIN_THREADS;
+        lo[k] = hi[k] = 0;
+        if (j < n_items) {
+            const uint2 r = __ldg(rect + __ldg(order + j));
+            lo[k] = (int)(r.x >> 16) - band_y0;
+            hi[k] = (int)(r.y >> 16) - band_y0;
+            if ((r.y & 0xFFFFu) <= (r.x & 0xFFFFu)) hi[k] = lo[k];      // culled: empty rectangle
+        }
+    }
+    count_cover(lo, hi, gy, row_count + (size_t)blockIdx.x * gy, s_diff, s_warp);
+}
 
-    const int base = blockIdx.x * EMIT_THREADS;
-    const int i = base + threadIdx.x;
-    const uint32_t block_start = base > 0 ? __ldg(offsets + base - 1) : 0u;
-    const int last = min(base + EMIT_THREADS, P) - 1;
-    const uint32_t total = __ldg(offsets + last) - block_start;
-    if (total == 0u) return;
+// rows, step 2: exclusive scan over chunks of every row's counts (one warp per row) -> each (chunk, row)'s base
+__global__ void __launch_bounds__(256)
+bin_scan_rows_kernel(int n_chunks, int gy, uint32_t* __restrict__ row_count, uint32_t* __restrict__ row_total)
+{
+    const int y = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const uint32_t lane = threadIdx.x & 31u;
+    if (y >= gy) return;
+    uint32_t running = 0u;
+    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
+        const int c = c0 + (int)lane;
+        const uint32_t v = c < n_chunks ? row_count[(size_t)c * gy + y] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += o;
+        }
+        if (c < n_chunks) row_count[(size_t)c * gy + y] = running + incl - v;
+        running += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) row_total[y] = running;
+}
 
-    if (i < P) {
-        const uint32_t g = __ldg(order + i);
-        s_end[threadIdx.x] = __ldg(offsets + i) - block_start;
-        s_id[threadIdx.x] = g;
-        s_rect[threadIdx.x] = __ldg(rect + g);
-    } else {
-        s_end[threadIdx.x] = total;
-        s_id[threadIdx.x] = 0u;
-        s_rect[threadIdx.x] = make_uint2(0u, 0u);
+// rows, step 3 (one block): where each row's run list starts, and which column sub-chunks (1024 runs) it is cut into
+__global__ void __launch_bounds__(1024)
+bin_row_offsets_kernel(int gy, const uint32_t* __restrict__ row_total, uint32_t* __restrict__ row_start,
+                       uint32_t* __restrict__ sub_first)
+{
+    __shared__ uint32_t s_warp[32];
+    uint32_t run_carry = 0u, sub_carry = 0u;
+    for (int y0 = 0; y0 < gy; y0 += 1024) {
+        const int y = y0 + (int)threadIdx.x;
+        const uint32_t t = y < gy ? row_total[y] : 0u;
+        uint32_t tot_runs, tot_subs;
+        const uint32_t e_runs = block_scan_excl<1024>(t, s_warp, tot_runs);
+        const uint32_t e_subs = block_scan_excl<1024>((t + BIN_CH - 1) / BIN_CH, s_warp, tot_subs);
+        if (y < gy) { row_start[y] = run_carry + e_runs; sub_first[y] = sub_carry + e_subs; }
+        run_carry += tot_runs; sub_carry += tot_subs;
+    }
+    if (threadIdx.x == 0) { row_start[gy] = run_carry; sub_first[gy] = sub_carry; }
+}
+
+// rows, step 4: every chunk writes its runs {id, x0 | x1 << 16} into the rows' run lists, in depth order
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_scatter_rows_kernel(int n_items, int gy, int band_y0, const uint32_t* __restrict__ order,
+                        const uint2* __restrict__ rect, const uint32_t* __restrict__ row_base,
+                        const uint32_t* __restrict__ row_start, uint2* __restrict__ runs)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t* s_lohi = s_dyn;                                     // y0 | y1 << 16 (band-relative)
+    uint2* s_pay = reinterpret_cast<uint2*>(s_dyn + BIN_CH);      // {id, x0 | x1 << 16}
+    uint32_t* s_bits = s_dyn + 3 * BIN_CH;
+    const int base = (int)blockIdx.x * BIN_CH;
+    const int n_local = min(BIN_CH, n_items - base);
+    for (int j = (int)threadIdx.x; j < BIN_CH; j += BIN_THREADS) {
+        uint32_t lh = 0u;
+        uint2 pay = make_uint2(0u, 0u);
+        if (j < n_local) {
+            const uint32_t g = __ldg(order + base + j);
+            const uint2 r = __ldg(rect + g);
+            const uint32_t x0 = r.x & 0xFFFFu, x1 = r.y & 0xFFFFu;
+            if (x1 > x0) lh = ((r.x >> 16) - (uint32_t)band_y0) | (((r.y >> 16) - (uint32_t)band_y0) << 16);
+            pay = make_uint2(g, x0 | (x1 << 16));
+        }
+        s_lohi[j] = lh;
+        s_pay[j] = pay;
     }
     __syncthreads();
-
-    for (uint32_t t = threadIdx.x; t < total; t += EMIT_THREADS) {
-        // smallest k with s_end[k] > t
-        int lo = 0;
-#pragma unroll
-        for (int step = EMIT_THREADS / 2; step > 0; step >>= 1)
-            if (s_end[lo + step - 1] <= t) lo += step;
-        const uint32_t start = lo > 0 ? s_end[lo - 1] : 0u;
-        const uint32_t local = t - start;
-        const uint2 r = s_rect[lo];
-        const uint32_t x0 = r.x & 0xFFFFu, y0 = r.x >> 16, x1 = r.y & 0xFFFFu;
-        const uint32_t w = x1 - x0;
-        const uint32_t ry = local / w, rx = local - ry * w;   // row-major over (y, x), rasterizer_impl.cu:96-99
-        tile_keys[block_start + t] = (KeyT)((y0 - band_y0 + ry) * (uint32_t)grid_x + (x0 + rx));   // band-relative tile id
-        ids[block_start + t] = s_id[lo];
-    }
+    const uint32_t* my_base = row_base + (size_t)blockIdx.x * gy;
+    scatter_cover<uint2>(n_local, s_lohi, s_pay, gy, s_bits, runs,
+                         [&](int y) { return __ldg(row_start + y) + __ldg(my_base + y); });
 }
 
-// ---- stage 2c: tile ranges -------------------------------------------------------------------
-// identifyTileRanges (rasterizer_impl.cu:116-138) on the sorted tile keys.  Each thread scans
-// KPT consecutive keys fetched with one 16-byte load (the reference: one thread, two scalar loads
-// per key), so the kernel streams at HBM rate; boundaries are rare (one per non-empty tile).
-template <typename KeyT>
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(uint32_t I, const KeyT* __restrict__ keys, uint2* __restrict__ ranges)
+// columns, step 1: per (sub-chunk of 1024 runs of one row, tile column) the number of runs covering the tile
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_count_cols_kernel(int gy, int gx, const uint32_t* __restrict__ sub_first, const uint32_t* __restrict__ row_start,
+                      const uint32_t* __restrict__ row_total, const uint2* __restrict__ runs,
+                      uint32_t* __restrict__ col_count)
 {
-    constexpr uint32_t KPT = 16 / sizeof(KeyT);               // keys per thread: 8 (u16) or 4 (u32)
-    const uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) * KPT;
-    if (base >= I) return;
-    KeyT k[KPT];
-    if (base + KPT <= I) {
-        *reinterpret_cast<uint4*>(k) = __ldg(reinterpret_cast<const uint4*>(keys + base));    // base*sizeof(KeyT) % 16 == 0
-    } else {
+    __shared__ int s_diff[BIN_WIN + 1];
+    __shared__ uint32_t s_warp[32];
+    int y; uint32_t beg, end;
+    if (!locate_sub(blockIdx.x, gy, sub_first, row_start, row_total, y, beg, end)) return;     // whole block
+    int lo[BIN_IPT], hi[BIN_IPT];
 #pragma unroll
-        for (uint32_t j = 0; j < KPT; j++) k[j] = base + j < I ? __ldg(keys + base + j) : (KeyT)0;
+    for (int k = 0; k < BIN_IPT; k++) {
+        const uint32_t j = beg + threadIdx.x + (uint32_t)k * BIN_THREADS;
+        lo[k] = hi[k] = 0;
+        if (j < end) {
+            const uint32_t xx = __ldg(&runs[j].y);
+            lo[k] = (int)(xx & 0xFFFFu);
+            hi[k] = (int)(xx >> 16);
+        }
     }
-    uint32_t prev = base > 0 ? (uint32_t)__ldg(keys + base - 1) : 0u;
-    if (base == 0) ranges[(uint32_t)k[0]].x = 0;
+    count_cover(lo, hi, gx, col_count + (size_t)blockIdx.x * gx, s_diff, s_warp);
+}
+
+// columns, step 2: exclusive scan over the sub-chunks of a row, per tile (one thread per tile); the total is the
+// tile's list length, parked in ranges[tile].y for the scan over tiles
+__global__ void __launch_bounds__(256)
+bin_scan_cols_kernel(int gy, int gx, const uint32_t* __restrict__ sub_first, uint32_t* __restrict__ col_count,
+                     uint2* __restrict__ ranges)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint32_t)gy * (uint32_t)gx) return;
+    const uint32_t y = t / (uint32_t)gx, x = t - y * (uint32_t)gx;
+    const uint32_t s0 = __ldg(sub_first + y), s1 = __ldg(sub_first + y + 1);
+    uint32_t acc = 0u;
+    for (uint32_t s = s0; s < s1; s++) {
+        const size_t i = (size_t)s * gx + x;
+        const uint32_t v = col_count[i];
+        col_count[i] = acc;
+        acc += v;
+    }
+    ranges[t] = make_uint2(0u, acc);
+}
+
+// columns, step 3 (one block): scan over tiles -> ranges[tile] = [start, end) of its list (identifyTileRanges,
+// rasterizer_impl.cu:116-138: empty tiles stay (0, 0))
+__global__ void __launch_bounds__(1024)
+bin_tile_ranges_kernel(uint32_t tiles, uint2* __restrict__ ranges)
+{
+    __shared__ uint32_t s_warp[32];
+    uint32_t carry = 0u;
+    for (uint32_t t0 = 0; t0 < tiles; t0 += 4096u) {
+        const uint32_t t = t0 + 4u * threadIdx.x;
+        uint32_t c[4];
 #pragma unroll
-    for (uint32_t j = 0; j < KPT; j++) {
-        const uint32_t idx = base + j;
-        if (idx >= I) break;
-        const uint32_t cur = (uint32_t)k[j];
-        if (idx > 0 && cur != prev) { ranges[prev].y = idx; ranges[cur].x = idx; }
-        if (idx == I - 1) ranges[cur].y = I;
-        prev = cur;
+        for (int k = 0; k < 4; k++) c[k] = t + k < tiles ? ranges[t + k].y : 0u;
+        uint32_t tot;
+        uint32_t start = carry + block_scan_excl<1024>(c[0] + c[1] + c[2] + c[3], s_warp, tot);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (t + k < tiles) ranges[t + k] = c[k] ? make_uint2(start, start + c[k]) : make_uint2(0u, 0u);
+            start += c[k];
+        }
+        carry += tot;
     }
 }
 
-// getHigherMsb (rasterizer_impl.cu:35-50): number of key bits needed for tile ids
-static uint32_t higher_msb(uint32_t n) {
-    uint32_t msb = sizeof(n) * 4, step = msb;
-    while (step > 1) {
-        step /= 2;
-        if (n >> msb) msb += step; else msb -= step;
+// columns, step 4: every sub-chunk writes the ids of its runs into the tiles' lists, in depth order
+__global__ void __launch_bounds__(BIN_THREADS)
+bin_scatter_cols_kernel(int gy, int gx, const uint32_t* __restrict__ sub_first, const uint32_t* __restrict__ row_start,
+                        const uint32_t* __restrict__ row_total, const uint2* __restrict__ runs,
+                        const uint32_t* __restrict__ col_base, const uint2* __restrict__ ranges,
+                        uint32_t* __restrict__ point_list)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t* s_lohi = s_dyn;                                     // x0 | x1 << 16
+    uint32_t* s_pay = s_dyn + BIN_CH;                             // Gaussian id
+    uint32_t* s_bits = s_dyn + 2 * BIN_CH;
+    int y; uint32_t beg, end;
+    if (!locate_sub(blockIdx.x, gy, sub_first, row_start, row_total, y, beg, end)) return;     // whole block
+    const int n_local = (int)(end - beg);
+    for (int j = (int)threadIdx.x; j < BIN_CH; j += BIN_THREADS) {
+        uint2 r = make_uint2(0u, 0u);
+        if (j < n_local) r = __ldg(runs + beg + j);
+        s_pay[j] = r.x;
+        s_lohi[j] = r.y;
     }
-    if (n >> msb) msb++;
-    return msb;
+    __syncthreads();
+    const uint32_t* my_base = col_base + (size_t)blockIdx.x * gx;
+    const uint2* row_ranges = ranges + (size_t)y * gx;
+    scatter_cover<uint32_t>(n_local, s_lohi, s_pay, gx, s_bits, point_list,
+                            [&](int x) { return __ldg(&row_ranges[x].x) + __ldg(my_base + x); });
 }
 
 int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, const char* geom,
                    const GeomLayout& GL, uint32_t* point_list, char* binning,
                    const BinningLayout& BL, char* image, const ImageLayout& IL)
 {
-    const int grid_x = (W + TILE - 1) / TILE;
-    const uint32_t tiles = (uint32_t)grid_x * (uint32_t)band.rows();
+    const int gx = (W + TILE - 1) / TILE, gy = band.rows();
+    const uint32_t tiles = (uint32_t)gx * (uint32_t)gy;
     uint2* ranges = reinterpret_cast<uint2*>(image + IL.ranges);
-    EOGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
-    if (I == 0) return 0;
-    if (I > 0x7FFFFFFFu) {        // cub::DeviceRadixSort takes a signed 32-bit item count
+    if (I == 0) {
+        EOGS_CUDA(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
+        return 0;
+    }
+    if (I > 0x7FFFFFFFu) {
         set_error("%u (Gaussian, tile) instances exceed 2^31-1: render the view in tile bands (eogs_*_band)", I);
         return -3;
     }
+    const uint32_t* order = reinterpret_cast<const uint32_t*>(geom + GL.order);
+    const uint2* rect = reinterpret_cast<const uint2*>(geom + GL.rect);
+    uint32_t* row_count = reinterpret_cast<uint32_t*>(binning + BL.row_count);
+    uint32_t* row_total = reinterpret_cast<uint32_t*>(binning + BL.row_total);
+    uint32_t* row_start = reinterpret_cast<uint32_t*>(binning + BL.row_start);
+    uint32_t* sub_first = reinterpret_cast<uint32_t*>(binning + BL.sub_first);
+    uint2* runs = reinterpret_cast<uint2*>(binning + BL.runs);
+    uint32_t* col_count = reinterpret_cast<uint32_t*>(binning + BL.col_count);
 
-    uint32_t* val_in = reinterpret_cast<uint32_t*>(binning + BL.val_in);
-    // The reference sorts bits [0, 32 + getHigherMsb(tiles)) (rasterizer_impl.cu:306-311); tile ids are
-    // < tiles, so the bits of tiles - 1 are all the significant ones and a stable sort over just those
-    // gives the identical order.  This matters exactly at powers of two: the 4096^2 sun view has 65 536
-    // tiles = 16 significant bits (two 8-bit passes on 16-bit keys), where getHigherMsb says 17.
-    const int bit = tiles > 1 ? (int)higher_msb(tiles - 1) : 1;
+    // Gaussians without a tile in this band sort behind every contributing one (key 0xFFFFFFFF, preprocess.cu) and
+    // every contributing one owns >= 1 instance: the first min(P, I) entries of the depth order hold all the work.
+    const int n_items = (int)min((uint32_t)P, I);
+    const int n_chunks = (n_items + BIN_CH - 1) / BIN_CH;
+    const uint32_t n_subs = I / BIN_CH + (uint32_t)gy + 1u;      // >= sum over rows of ceil(runs / 1024)
+    if ((size_t)n_chunks > BL.chunk_cap || (size_t)n_subs > BL.sub_cap) { set_error("binning scratch too small"); return -3; }
 
-    // Tile ids fit 16 bits up to 65 536 tiles (4096^2 images): 16-bit sort keys cut the traffic of
-    // every sort pass from 16 to 12 bytes per instance.  Larger grids sort 32-bit keys.
-    auto run = [&](auto key_tag) -> int {
-        using KeyT = decltype(key_tag);
-        KeyT* key_in = reinterpret_cast<KeyT*>(binning + BL.key_in);
-        KeyT* key_out = reinterpret_cast<KeyT*>(binning + BL.key_out);
-        // An onesweep sort of `bit` bits takes ceil(bit/8) passes and ping-pongs between the two value
-        // buffers: emit into the one that makes the LAST pass land in point_list (no copy afterwards).
-        const bool even_passes = (((bit + 7) / 8) & 1) == 0;
-        uint32_t* ids_first = even_passes ? point_list : val_in;
-        uint32_t* ids_other = even_passes ? val_in : point_list;
-        emit_instances_kernel<KeyT><<<(P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, s>>>(
-            P, grid_x, (uint32_t)band.row_begin, reinterpret_cast<const uint32_t*>(geom + GL.order),
-            reinterpret_cast<const uint32_t*>(geom + GL.offsets),
-            reinterpret_cast<const uint2*>(geom + GL.rect), key_in, ids_first);
-        EOGS_LAUNCH_CHECK("emit_instances_kernel");
-        prof_mark(s, ST_EMIT);
+    const size_t smem_rows = (size_t)(3 * BIN_CH + min(gy, BIN_WIN) * BIN_ROW) * 4;
+    const size_t smem_cols = (size_t)(2 * BIN_CH + min(gx, BIN_WIN) * BIN_ROW) * 4;
+    static_assert((3 * BIN_CH + BIN_WIN * BIN_ROW) * 4 <= 227 * 1024, "bitmap window too large");
+    EOGS_CUDA(cudaFuncSetAttribute(bin_scatter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    EOGS_CUDA(cudaFuncSetAttribute(bin_scatter_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
 
-        cub::DoubleBuffer<KeyT> keys(key_in, key_out);
-        cub::DoubleBuffer<uint32_t> vals(ids_first, ids_other);
-        size_t need = 0;
-        EOGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, (int)I, 0, bit, s));
-        if (need > BL.temp_bytes) { set_error("tile sort temp %zu > %zu", need, BL.temp_bytes); return -3; }
-        need = BL.temp_bytes;
-        EOGS_CUDA(cub::DeviceRadixSort::SortPairs(binning + BL.temp, need, keys, vals, (int)I, 0, bit, s));
-        if (vals.Current() != point_list)
-            EOGS_CUDA(cudaMemcpyAsync(point_list, vals.Current(), (size_t)I * 4, cudaMemcpyDeviceToDevice, s));
-        prof_mark(s, ST_TILE_SORT);
+    bin_count_rows_kernel<<<n_chunks, BIN_THREADS, 0, s>>>(n_items, gy, band.row_begin, order, rect, row_count);
+    EOGS_LAUNCH_CHECK("bin_count_rows_kernel");
+    bin_scan_rows_kernel<<<(gy * 32 + 255) / 256, 256, 0, s>>>(n_chunks, gy, row_count, row_total);
+    EOGS_LAUNCH_CHECK("bin_scan_rows_kernel");
+    bin_row_offsets_kernel<<<1, 1024, 0, s>>>(gy, row_total, row_start, sub_first);
+    EOGS_LAUNCH_CHECK("bin_row_offsets_kernel");
+    bin_scatter_rows_kernel<<<n_chunks, BIN_THREADS, smem_rows, s>>>(n_items, gy, band.row_begin, order, rect, row_count,
+                                                                      row_start, runs);
+    EOGS_LAUNCH_CHECK("bin_scatter_rows_kernel");
+    prof_mark(s, ST_BIN_ROWS);
 
-        constexpr uint32_t per_block = 256u * (16u / sizeof(KeyT));
-        tile_ranges_kernel<KeyT><<<(I + per_block - 1) / per_block, 256, 0, s>>>(I, keys.Current(), ranges);
-        EOGS_LAUNCH_CHECK("tile_ranges_kernel");
-        return 0;
-    };
-    if (int rc = tiles <= 0x10000u ? run(uint16_t{}) : run(uint32_t{})) return rc;
-    prof_mark(s, ST_RANGES);
+    bin_count_cols_kernel<<<n_subs, BIN_THREADS, 0, s>>>(gy, gx, sub_first, row_start, row_total, runs, col_count);
+    EOGS_LAUNCH_CHECK("bin_count_cols_kernel");
+    bin_scan_cols_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(gy, gx, sub_first, col_count, ranges);
+    EOGS_LAUNCH_CHECK("bin_scan_cols_kernel");
+    bin_tile_ranges_kernel<<<1, 1024, 0, s>>>(tiles, ranges);
+    EOGS_LAUNCH_CHECK("bin_tile_ranges_kernel");
+    prof_mark(s, ST_BIN_COUNT);
+
+    bin_scatter_cols_kernel<<<n_subs, BIN_THREADS, smem_cols, s>>>(gy, gx, sub_first, row_start, row_total, runs, col_count,
+                                                                    ranges, point_list);
+    EOGS_LAUNCH_CHECK("bin_scatter_cols_kernel");
+    prof_mark(s, ST_BIN_SCATTER);
     return 0;
 }
 

@@ -34,8 +34,7 @@ struct GeomLayout {
     size_t key_out;      // u32[P]
     size_t id_in;        // u32[P]       0..P-1
     size_t order;        // u32[P]       Gaussian ids sorted by (depth bits, id)
-    size_t offsets;      // u32[P]       inclusive scan of tiles[order[i]]
-    size_t temp;         // CUB temp storage (depth sort, scan)
+    size_t temp;         // CUB temp storage (depth sort)
     size_t temp_bytes;
     size_t total;
 };
@@ -62,12 +61,14 @@ struct Band {
     __host__ __device__ int height(int H) const { return (row_end * TILE < H ? row_end * TILE : H) - row_begin * TILE; }
 };
 
-struct BinningLayout {
-    size_t key_in;       // u32[I] tile id per instance (emission order)
-    size_t key_out;      // u32[I]
-    size_t val_in;       // u32[I] Gaussian id per instance
-    size_t temp;
-    size_t temp_bytes;
+struct BinningLayout {       // scratch of the tile-list construction (binning.cu), freed after the forward
+    size_t row_count;    // u32[chunks][band rows]   runs per (chunk of 1024 depth-ordered Gaussians, tile row) -> exclusive bases
+    size_t row_total;    // u32[rows + 1]            runs per tile row
+    size_t row_start;    // u32[rows + 1]            where the row's run list starts in `runs`
+    size_t sub_first;    // u32[rows + 1]            first column sub-chunk (1024 runs) of the row
+    size_t runs;         // uint2[<= I]              {Gaussian id, x0 | x1 << 16}, per row in depth order
+    size_t col_count;    // u32[sub-chunks][grid_x]  runs covering a tile per sub-chunk -> exclusive bases
+    size_t chunk_cap, sub_cap;
     size_t total;
 };
 
@@ -98,7 +99,7 @@ int cuda_fail(cudaError_t e, const char* what);
 // When enabled on the calling thread, every stage boundary records a CUDA event on the launch
 // stream; eogs_profile_read() synchronises and returns the elapsed milliseconds per stage.
 enum Stage : int {
-    ST_BEGIN = 0, ST_PREPROCESS, ST_DEPTH_SORT, ST_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_BLEND_FWD,
+    ST_BEGIN = 0, ST_PREPROCESS, ST_DEPTH_SORT, ST_BIN_ROWS, ST_BIN_COUNT, ST_BIN_SCATTER, ST_BLEND_FWD,
     ST_BWD_ZERO, ST_BLEND_BWD, ST_PREPROCESS_BWD, ST_COUNT
 };
 void prof_begin(cudaStream_t s);

@@ -136,7 +136,9 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
                 out_tiles = area_band;
                 out_rect = make_uint2((uint32_t)x0 | ((uint32_t)y0b << 16), (uint32_t)x1 | ((uint32_t)y1b << 16));
                 out_depth = d;
-                out_key = __float_as_uint(d);
+                // sort key: depth bits; a Gaussian without a tile in THIS band sorts behind every contributing one, like the
+                // culled ones, so that the first min(P, I) entries of the depth order hold all the work of the binning
+                out_key = area_band != 0u ? __float_as_uint(d) : 0xFFFFFFFFu;
                 float op_in = __ldg(opacities + idx);
                 if (RAW) op_in = act_sigmoid(op_in);
                 const float op = __fmul_rn(op_in, aa_scale);

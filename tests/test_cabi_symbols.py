@@ -49,7 +49,7 @@ def test_size_queries_are_host_only_and_monotonic():
     g1, g2 = lib.eogs_geom_bytes(1000), lib.eogs_geom_bytes(1_000_000)
     assert 0 < g1 < g2 and g2 >= 1_000_000 * (48 + 4 + 8 + 4 * 6)
     assert lib.eogs_image_bytes(2048, 2048) >= 2048 * 2048 * 8 + 16384 * 8
-    assert lib.eogs_binning_bytes(2048, 2048, 10_000_000) >= 10_000_000 * 12
+    assert lib.eogs_binning_bytes(2048, 2048, 10_000_000) >= 10_000_000 * 8      # one 8-byte run per instance at most
     assert lib.eogs_geom_bytes(0) > 0
 
 
