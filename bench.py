@@ -59,52 +59,53 @@ def dist_env():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region, every 5 ms through NVML on a host thread (the
+    timed region of a default run lasts ~60 ms: `nvidia-smi -lms` would not deliver a single sample in it, which is
+    why the lines of round 1 carried `samples: 0` under torchrun).  One sampler per rank, on that rank's GPU."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.gpu, self.sm, self.reasons, self.mx, self.power = gpu_index, [], set(), None, []
+        self._stop = threading.Event()
+        self.t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[gpu_index]) if visible and visible.split(",")[gpu_index].isdigit() else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:                                   # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for name, bit in self.REASONS:
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:                               # noqa: BLE001
+                pass
+            self._stop.wait(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+        if self.nv is not None:
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self._stop.set()
+        if self.t is not None:
+            self.t.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None, "source": "NVML, 5 ms period, during the timed regions"}
 
 
 def make_workload(dev, rank: int):
@@ -186,10 +187,16 @@ def ours_e2e_factory(wl, dev, world=1):
     names = ["means3D", "scales", "rotations", "opacities", "colors"]
     h2d = sum(h[k].numel() * 4 for k in names)
     out_host = torch.zeros(17, dtype=torch.float32).pin_memory()
-    from eogs2_b200.dp import HostInputPipeline
+    from eogs2_b200.dp import GradBucket, HostInputPipeline
     hsub = {k: h[k] for k in names}
     pipe = HostInputPipeline(dev)
     pipe.submit(hsub)                       # inputs of the first step; every step submits the next one's
+    bucket = None
+    if world > 1:
+        # data parallel over views through the package's own exchange path: ONE flat bucket (16-byte aligned segments),
+        # gradients packed into it, all-reduced by the NVLS kernel or ncclAllReduce (whichever calibrates faster)
+        shapes = {k: torch.empty_like(h[k], device=dev) for k in names}
+        bucket = GradBucket(shapes, {"viewmatrix": torch.empty(4, 4, device=dev)}, exchange="auto")
 
     def step():
         bufs = pipe.get()                   # this step's inputs (copied from pinned host memory on the side stream)
@@ -206,18 +213,20 @@ def ours_e2e_factory(wl, dev, world=1):
         pipe.submit(hsub)                   # next step's H2D (one copy per step) overlaps this step's blend kernels
         loss = (color * wl["dcol"]).sum()
         loss.backward()
-        if world > 1:
-            # data parallel over views: the step is not finished before the gradients are summed over ranks
-            import torch.distributed as dist
-            flat = torch.cat([t[k].grad.reshape(-1) for k in names] + [view.grad.reshape(-1)])
-            dist.all_reduce(flat)
-            view_grad = flat[-16:]
+        if bucket is not None:
+            # the step is not finished before the gradients are summed over ranks
+            bucket.params, bucket.extras = t, {"viewmatrix": view}
+            bucket.pack()
+            flat = bucket.all_reduce()
+            a, b = bucket.slices["extra:viewmatrix"]
+            view_grad = flat[a:b]
         else:
             view_grad = view.grad.reshape(-1)
         res = torch.cat([loss.detach().reshape(1), view_grad])
         out_host.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(out_host[0])
+    step.exchange_name = bucket.exchange_name if bucket is not None else None
     return step, h2d, out_host.numel() * 4
 
 
@@ -290,11 +299,22 @@ def timed_steps(step, steps, warmup, flush, world, post=None):
         dist.barrier()
     wall = time.perf_counter() - t0
     total_ms = sum(s.elapsed_time(e) for s, e in evs)
+    timed_steps.local_ms = total_ms                      # this rank's own device time (per-rank report at N > 1)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     return total_ms, wall
+
+
+def gather_to_rank0(obj, world):
+    """Small Python objects of every rank, as a list on rank 0 (None elsewhere)."""
+    if world == 1:
+        return [obj]
+    import torch.distributed as dist
+    out = [None] * world if dist.get_rank() == 0 else None
+    dist.gather_object(obj, out, dst=0)
+    return out
 
 
 def cpu_baseline(wl, seconds_hint=20.0):
@@ -332,6 +352,182 @@ def cpu_baseline(wl, seconds_hint=20.0):
 
 
 # ----------------------------------------------------------------------------------------------
+def count_pairs():
+    """Evaluated / blended (pixel, Gaussian) pairs of ONE fwd+bwd render of the bench workload (SURVEY.md section 8d:
+    "always report pairs_eval, pairs_blend"), counted by the instrumented twin of the library
+    (libeogs_raster_count.so, -DEOGS_COUNT_PAIRS=1) in a child process — never inside a timed region, never with
+    the product library."""
+    from eogs2_b200.build import COUNT_LIB
+    if not COUNT_LIB.exists():
+        return {"unavailable": f"{COUNT_LIB.name} not built"}
+    env = dict(os.environ, EOGS_RASTER_LIB=str(COUNT_LIB))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--count-pairs-child"], env=env, capture_output=True,
+                           text=True, timeout=300)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:                                  # noqa: BLE001
+        return {"unavailable": f"counting run failed: {e}"}
+
+
+def count_pairs_child():
+    import eogs2_b200 as E
+    from eogs2_b200 import _cabi
+    lib = _cabi.load()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    wl = make_workload(dev, 0)
+    buf = (ctypes.c_ulonglong * 16)()
+    if lib.eogs_debug_counters(buf, 1) != 1:
+        print(json.dumps({"unavailable": "library built without EOGS_COUNT_PAIRS"}))
+        return 0
+    st, _ = ours_step_factory(wl, dev)()
+    torch.cuda.synchronize()
+    lib.eogs_debug_counters(buf, 1)
+    names = ["fwd_pairs_eval", "fwd_pairs_blend", "fwd_lane_slots", "fwd_entries", "bwd_pairs_eval", "bwd_pairs_blend",
+             "bwd_lane_slots", "bwd_entries", "bwd_flushes"]
+    print(json.dumps(dict({n: int(buf[i]) for i, n in enumerate(names)}, instances=st.num_rendered)))
+    return 0
+
+
+def ncu_record():
+    """The committed ncu capture of the CURRENT kernels, if any: profiles/ncu_current.json is written by
+    tools/ncu_to_json.py from a `ncu --set full` report of this same command, together with the hash of the CUDA
+    sources it was taken from; a capture of other sources is not quoted."""
+    from eogs2_b200.build import source_hash
+    f = ROOT / "profiles" / "ncu_current.json"
+    if not f.exists():
+        return None, "no profiles/ncu_current.json"
+    rec = json.loads(f.read_text())
+    if rec.get("source_hash") != source_hash():
+        return None, "profiles/ncu_current.json was captured from different kernel sources (hash mismatch): not quoted"
+    return rec, f"profiles/ncu_current.json ({rec.get('report', '?')})"
+
+
+def roofline_report(stage_ms, I, peaks, hbm_peak, peak_src, clocks):
+    """Dominant kernel = blend backward.  The contract's HBM figure (algorithmic bytes / CUDA-event time / measured
+    copy bandwidth) plus what actually bounds the kernel: instruction issue and FP32 rate (SURVEY.md section 8d:
+    "report both; the binding one is the roofline fraction")."""
+    bwd_ms = stage_ms[STAGES.index("blend_bwd")]
+    fwd_ms = stage_ms[STAGES.index("blend_fwd")]
+    # Algorithmic bytes per launch (DESIGN.md section 4): per instance 4 B id + 48 B record + 4 B alpha_cut gathered + 44 B
+    # (11 floats) reduced into the gradient record; per pixel 4*(C+1) B upstream gradient + 8 B final_T / n_contrib.
+    bwd_bytes = I * (4 + 48 + 4 + 44) + IMG * IMG * (4 * 6 + 8)
+    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
+    pairs = count_pairs()
+    rec, rec_src = ncu_record()
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    n_sm = 148
+    fp32_peak = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12        # TFLOP/s at the SM clock sampled during the run
+    out = {"kernel": "blend_bwd_kernel<5>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+           "frac": achieved / hbm_peak, "peak_source": peak_src, "ms_per_launch": bwd_ms, "algorithmic_bytes": bwd_bytes,
+           "traffic": None, "traffic_source": rec_src, "pairs": pairs,
+           "binding": "instruction issue (see issue_frac): DRAM traffic is a fraction of the algorithmic bytes because the "
+                      "48 MB record array is gathered out of L2 and entries behind a tile's last contributor are never "
+                      "fetched; the HBM fraction is reported because the contract asks for it"}
+    if "bwd_pairs_blend" in pairs:
+        # FLOP model of SURVEY.md section 8d: forward 11 FLOP per evaluated pair + 16 per blended pair (C = 5 + inverse depth),
+        # backward 2.2 x the forward's
+        f_flop = pairs["fwd_pairs_eval"] * 11 + pairs["fwd_pairs_blend"] * 16
+        b_flop = 2.2 * (pairs["bwd_pairs_eval"] * 11 + pairs["bwd_pairs_blend"] * 16)
+        out["fp32_peak_tflops"] = fp32_peak
+        out["fp32_frac"] = b_flop / (bwd_ms * 1e-3) / 1e12 / fp32_peak if bwd_ms > 0 else None
+        out["fwd"] = {"kernel": "blend_fwd_kernel<5>", "ms_per_launch": fwd_ms,
+                      "fp32_frac": f_flop / (fwd_ms * 1e-3) / 1e12 / fp32_peak if fwd_ms > 0 else None}
+    if rec is not None:
+        k = rec["kernels"].get("blend_bwd_kernel", {})
+        out["traffic"] = k.get("dram_bytes")
+        issue_slots = n_sm * 4 * sm_mhz * 1e6 * bwd_ms * 1e-3
+        if k.get("inst_executed"):
+            out["issue_frac"] = k["inst_executed"] / issue_slots          # warp instructions / issue slots of THIS run's launch time
+            out["issue_active_pct_ncu"] = k.get("issue_active_pct")
+            out["warps_active_per_sm_ncu"] = k.get("warps_active_per_sm")
+            if pairs.get("bwd_pairs_blend"):
+                out["thread_inst_per_blended_pair"] = 32.0 * k["inst_executed"] / pairs["bwd_pairs_blend"]
+        kf = rec["kernels"].get("blend_fwd_kernel", {})
+        if kf.get("inst_executed") and "fwd" in out:
+            out["fwd"]["issue_frac"] = kf["inst_executed"] / (n_sm * 4 * sm_mhz * 1e6 * fwd_ms * 1e-3)
+            out["fwd"]["traffic"] = kf.get("dram_bytes")
+            if pairs.get("fwd_pairs_blend"):
+                out["fwd"]["thread_inst_per_blended_pair"] = 32.0 * kf["inst_executed"] / pairs["fwd_pairs_blend"]
+    return out
+
+
+def config5_leg(dev, rank, world, flush, reps=3):
+    """BASELINE configs[4]: 5 M Gaussians, one 8192 x 8192 nadir altitude/DSM render (forward), tile rows sharded
+    over the N GPUs (eogs2_b200/bands.py: instance-balanced bands, one all-gather of the image); at N = 1 the image is
+    rendered as consecutive bands on the one GPU.  Device-timed, max over ranks, all-gather included."""
+    import eogs2_b200 as E
+    from eogs2_b200 import bands as B
+    from eogs2_b200 import scene as S
+    import torch.distributed as dist
+    P5, IMG5 = 5_000_000, 8192
+    try:
+        sc = S.make_scene(P5, "trained", SEED)
+        A = torch.tensor([[1 / 0.72, 0, 0], [0, 1 / 0.72, 0], [0, 0, S.METRES_PER_UNIT]])      # nadir camera
+        view = S.affine_to_viewmatrix(A, torch.zeros(3))
+        colors = S.colors_precomp(sc, view).to(dev)
+        view = view.to(dev)
+        t = {k: getattr(sc, k).to(dev) for k in ("means3D", "scales", "rotations", "opacities")}
+        bg = S.background(SEED).to(dev)
+        empty = torch.empty(0, device=dev)
+        grid_y = (IMG5 + 15) // 16
+        lib = E._cabi.load()
+
+        def render(weights=None):
+            if world == 1:
+                return B.forward_strips(bg, t["means3D"], colors, t["opacities"], t["scales"], t["rotations"], 1.0, empty,
+                                        view, IMG5, IMG5, max_tiles=65536)
+            return B.forward_band(bg, t["means3D"], colors, t["opacities"], t["scales"], t["rotations"], 1.0, empty, view,
+                                  IMG5, IMG5, rank, world, weights=weights)
+        weights, inst = None, None
+        out = render()
+        if world > 1:
+            st = out[2]
+            r = E.export_state(st)["ranges"].to(torch.int64)
+            per_row = (r[:, 1] - r[:, 0]).view(-1, (IMG5 + 15) // 16).sum(1)
+            all_rows = torch.zeros(grid_y, dtype=torch.int64, device=dev)
+            all_rows[st.rows[0]:st.rows[1]] = per_row
+            dist.all_reduce(all_rows)
+            weights, inst = all_rows.cpu().tolist(), int(all_rows.sum().item())
+        del out
+        render(weights)
+        ts, stages = [], [0.0] * len(STAGES)
+        buf = (ctypes.c_float * 16)()
+        for _ in range(reps):
+            flush()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); out = render(weights); e.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            ts.append(float(ms.item()))
+            checksum = float(out[0][3].double().abs().sum().item())
+            del out
+        if world > 1:                                          # this rank's band, stage by stage (rank 0 reports its own)
+            lib.eogs_profile_enable(1)
+            flush(); render(weights)
+            lib.eogs_profile_read(buf, 16)
+            lib.eogs_profile_enable(0)
+            stages = [buf[i] for i in range(len(STAGES))]
+        res = {"ms": statistics.median(ts), "P": P5, "W": IMG5, "H": IMG5, "passes": "forward, 5 channels + inverse depth",
+               "sharding": f"{world} instance-balanced tile bands + one all-gather" if world > 1 else
+                           "one GPU: consecutive bands of <= 65 536 tiles",
+               "instances": inst, "altitude_checksum": checksum, "max_over_ranks": world > 1}
+        if world > 1:
+            res["rank0_stage_ms"] = {STAGES[i]: round(stages[i], 3) for i in range(1, 7)}
+        return res
+    except Exception as ex:                                    # noqa: BLE001 — the headline line must survive this leg
+        return {"ms": None, "error": str(ex)[:300]}
+    finally:
+        torch.cuda.empty_cache()
+
+
 _REAL_STDOUT = None
 
 
@@ -352,7 +548,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the e2e leg (the line then carries e2e=null)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 5 M / 8192^2 tile-band leg (config5_ms)")
+    ap.add_argument("--count-pairs-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.count_pairs_child:
+        return count_pairs_child()
     args.warmup = max(args.warmup, 3)
     rank, world, local = dist_env()
 
@@ -431,7 +631,9 @@ def main():
     lib = _cabi.load()
     step = ours_step_factory(wl, dev)
     post = None
-    bucket = None
+    exchange = exchange_name = None
+    d = wl["dev"]
+    empty = torch.empty(0, device=dev)
     if world > 1:
         import torch.distributed as dist
         # ONE flat fp32 bucket holds every gradient the rasterizer returns for the replicated parameters —
@@ -446,27 +648,26 @@ def main():
         views = {"means3D": bucket[0:3 * P].view(P, 3), "colors": bucket[3 * P:8 * P].view(P, 5),
                  "opacity": bucket[8 * P:9 * P].view(P, 1), "scales": bucket[9 * P:12 * P].view(P, 3),
                  "rotations": bucket[12 * P:16 * P].view(P, 4), "cam_sums": bucket[16 * P:]}
-        d = wl["dev"]
-        empty = torch.empty(0, device=dev)
 
-        def step_dp():
-            st = E.rasterize_forward_raw(wl["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"],
-                                         d["rotations"], 1.0, empty, wl["view"], IMG, IMG, False, False)
-            g = E.rasterize_backward_raw(st, wl["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"],
-                                         d["rotations"], 1.0, empty, wl["view"], wl["view"], wl["dcol"], wl["dinv"],
-                                         out=views)
-            return st, g
+        def make_step_dp(view, dcol, dinv, colors):
+            def step_dp():
+                st = E.rasterize_forward_raw(wl["bg"], d["means3D"], colors, d["opacities"], d["scales"],
+                                             d["rotations"], 1.0, empty, view, IMG, IMG, False, False)
+                g = E.rasterize_backward_raw(st, wl["bg"], d["means3D"], colors, d["opacities"], d["scales"],
+                                             d["rotations"], 1.0, empty, view, view, dcol, dinv, out=views)
+                return st, g
+            return step_dp
 
         def post():
             exchange()
-        run_step = step_dp
+        run_step = make_step_dp(wl["view"], wl["dcol"], wl["dinv"], d["colors"])
         base["config"]["allreduce"] = exchange_name
     else:
         run_step = step
 
     sampler.start()
     total_ms, wall = timed_steps(run_step, args.steps, args.warmup, flush, world, post)
-    clocks = sampler.stop()
+    local_ms = timed_steps.local_ms
 
     # per-stage device times (CUDA events recorded inside the library on the launch stream)
     lib.eogs_profile_enable(1)
@@ -494,41 +695,68 @@ def main():
     it_steps = max(3, min(args.steps, 10))
     iter_ms, _ = timed_steps(iteration_factory(wl, dev, rank, "ours"), it_steps, 3, flush, world, post)
 
+    extra = {}
+    if world > 1:
+        import torch.distributed as dist
+        from eogs2_b200 import scene as S
+        # (1) pure weak scaling: EVERY rank renders rank 0's camera, so the step differs from the 1-GPU step only by
+        #     the exchange and the barrier skew — no workload variance between cameras
+        v0 = S.make_camera(SEED)
+        dcol0, dinv0 = S.upstream_grads(5, IMG, IMG, SEED, False)
+        same = make_step_dp(v0.to(dev), dcol0.to(dev), dinv0.to(dev), S.colors_precomp(wl["sc"], v0).to(dev))
+        same_ms, _ = timed_steps(same, args.steps, args.warmup, flush, world, post)
+        noex_ms, _ = timed_steps(same, args.steps, args.warmup, flush, world, None)
+        # (2) the exchange alone, and a bit check of the own kernel against ncclAllReduce on the same data
+        ex_ms, _ = timed_steps(lambda: None, args.steps, args.warmup, lambda: None, world, post)
+        check = None
+        if exchange_name.startswith("own NVLS"):
+            gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+            pattern = torch.randn(bucket.numel(), device=dev, generator=gen)
+            bucket.copy_(pattern); exchange(); mine = bucket.clone()
+            ref = pattern.clone(); dist.all_reduce(ref)
+            check = "bit-identical to ncclAllReduce" if torch.equal(mine, ref) else \
+                f"max |own - nccl| = {float((mine - ref).abs().max()):.3e} (summation order differs)"
+        extra["dp"] = {
+            "e2e_exchange": getattr(e2e_step, "exchange_name", None),
+            "per_rank": gather_to_rank0({"rank": rank, "camera_seed": SEED + rank, "instances": I,
+                                         "ms_per_step_local": local_ms / args.steps}, world),
+            "same_camera": {"ms_per_step": same_ms / args.steps, "value": world * args.steps / (same_ms / 1e3),
+                            "ms_per_step_without_exchange": noex_ms / args.steps,
+                            "what": "every rank renders camera 1337: weak scaling without workload variance"},
+            "exchange_ms": ex_ms / args.steps, "exchange_bytes": bucket.numel() * 4, "exchange_check": check}
+    clocks = sampler.stop()
+    all_clocks = gather_to_rank0(clocks, world)
+    if rank == 0 and world > 1:
+        ok = [c for c in all_clocks if c and c.get("sm_mhz")]
+        clocks = dict(clocks, per_rank_sm_mhz=[c.get("sm_mhz") for c in all_clocks],
+                      sm_mhz=min(c["sm_mhz"] for c in ok) if ok else None,
+                      reasons=sorted(set(r for c in all_clocks if c for r in c.get("reasons", []))),
+                      samples=sum(c.get("samples", 0) for c in all_clocks if c))
+
+    # config 5 (BASELINE configs[4]): 5 M Gaussians, 8192^2 forward, tile rows sharded over the N GPUs + all-gather
+    c5 = None if args.no_config5 else config5_leg(dev, rank, world, flush)
+
     value = world * args.steps / (total_ms / 1e3)
-    # roofline of the dominant kernel: blend backward.  Algorithmic bytes per launch:
-    # per instance 4 B id + 48 B record + 4 B alpha_cut gathered + 44 B (11 floats) reduced into the gradient record;
-    # per pixel 4*(C+1) B upstream gradient + 8 B final_T / n_contrib.
-    bwd_bytes = I * (4 + 48 + 4 + 44) + IMG * IMG * (4 * 6 + 8)
-    bwd_ms = stage_ms[STAGES.index("blend_bwd")]
-    achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9 if bwd_ms > 0 else 0.0
-    # DRAM traffic of one launch from the committed `ncu --set full` capture of this same command
-    # (profiles/r03y_blend_full.txt: dram__bytes_read.sum 263.80 MB + dram__bytes_write.sum 23.77 MB).  It is far
-    # BELOW the algorithmic bytes: records are gathered from L2 (126 MB holds the 48 MB record array) and list
-    # entries behind the tile's last contributor are never fetched — the kernel is not HBM-bound.
-    NCU_BWD_TRAFFIC = 263_800_064 + 23_765_760
     line = dict(base, value=value, ms_per_step=total_ms / args.steps, clocks=clocks,
                 e2e=None if e2e_ms is None else {"value": world * args.steps / (e2e_ms / 1e3), "unit": "renders/s",
                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                # preprocess, emit, tile ranges, blend fwd, blend bwd, preprocess bwd (+ the NVLS all-reduce kernel when it
-                # is the chosen exchange); CUB sorts / scans and torch's barrier kernels are not counted
-                gpu_launches=(6 + (1 if world > 1 and exchange_name.startswith("own NVLS") else 0)) * args.steps,
-                roofline={"kernel": "blend_bwd_kernel<5>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": NCU_BWD_TRAFFIC, "peak_source": peak_src,
-                          "ms_per_launch": bwd_ms, "algorithmic_bytes": bwd_bytes,
-                          "traffic_source": "profiles/r03y_blend_full.txt (ncu --set full, same workload)",
-                          "issue_active_pct_ncu": 63.7,
-                          "note": "issue-bound, not HBM-bound: ncu smsp__issue_active 64 % with 16 resident warps/SM "
-                                  "(register + shared-memory limited), DRAM throughput 2 % of peak; the HBM fraction is "
-                                  "reported because the contract asks for it, the binding ceiling is the issue rate "
-                                  "(DESIGN.md §4)"},
                 stage_ms={STAGES[i]: round(stage_ms[i], 4) for i in range(1, len(STAGES))},
                 iter_ms=iter_ms / it_steps,
                 iter_pattern="one camera per rank: main 2048^2 + sun 4096^2 + random 2048^2, fwd+bwd each"
                              + (", then the gradient all-reduce" if world > 1 else ""),
-                instances=I, wall_s=wall)
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(wl)
+                instances=I, wall_s=wall, **extra)
+    if c5 is not None:
+        line["config5_ms"] = c5["ms"]
+        line["config5"] = c5
     if rank == 0:
+        # preprocess, 4 binning passes (count / scan / offsets / scatter) x rows and columns, blend fwd, tile order,
+        # blend bwd, preprocess bwd (+ the NVLS all-reduce kernel when it is the chosen exchange); the CUB depth sort
+        # and torch's fill / barrier kernels are not counted
+        own = 1 + 8 + 2 + 2 + (1 if world > 1 and exchange_name.startswith("own NVLS") else 0)
+        line["gpu_launches"] = own * args.steps
+        line["roofline"] = roofline_report(stage_ms, I, peaks, hbm_peak, peak_src, clocks)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
         emit(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

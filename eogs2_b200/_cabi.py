@@ -99,6 +99,7 @@ SIGNATURES = {
     "eogs_mark_visible": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_f32p, c_ptr]),
     "eogs_profile_enable": (C.c_int, [C.c_int]),
     "eogs_profile_read": (C.c_int, [c_ptr, C.c_int]),
+    "eogs_debug_counters": (C.c_int, [c_ptr, C.c_int]),
     "eogs_debug_alpha_cut": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_ptr]),
     "eogs_export_state": (C.c_int, [
         c_ptr, C.c_int, C.c_int, C.c_int, C.c_uint32, c_ptr, c_ptr, c_ptr,

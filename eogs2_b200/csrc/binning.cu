@@ -29,6 +29,18 @@ namespace eogs {
 
 size_t sort_temp_bound(size_t n) { return (size_t(1) << 20) + n; }
 
+int sm_count_cached() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached = n; cached_dev = dev;
+    }
+    return cached;
+}
+
 GeomLayout geom_layout(int P) {
     GeomLayout L;
     const size_t n = (size_t)(P > 0 ? P : 1);
@@ -82,6 +94,8 @@ constexpr int BIN_THREADS = 256;
 constexpr int BIN_IPT = BIN_CH / BIN_THREADS; // items per thread
 constexpr int BIN_WIN = 1024;                // tile rows (columns) per shared-memory window
 constexpr int BIN_ROW = BIN_WORDS + 1;       // bitmap row stride in words: rows land in distinct banks
+constexpr int BIN_BWIN = 256;                // bins per bitmap window of the scatter kernels (bounds their shared memory)
+constexpr int BIN_PRE = 2 * (BIN_WORDS / 2 + 1);   // halves per row of the word-prefix table (17 words: odd stride)
 
 BinningLayout binning_layout(int W, int H, uint32_t I) {
     BinningLayout L;
@@ -159,24 +173,31 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t* s_warp
     return wbase + incl - v;
 }
 
-// Which column sub-chunk is block `s`: row y with sub_first[y] <= s < sub_first[y + 1], runs [beg, end) of that row.
-__device__ __forceinline__ bool locate_sub(uint32_t s, int gy, const uint32_t* __restrict__ sub_first,
-                                           const uint32_t* __restrict__ row_start, const uint32_t* __restrict__ row_total,
-                                           int& y, uint32_t& beg, uint32_t& end) {
-    if (s >= __ldg(sub_first + gy)) return false;
+// Which column sub-chunk is `s`: row y with sub_first[y] <= s < sub_first[y + 1], runs [beg, end) of that row.
+// sub_first (one entry per tile row) is staged in shared memory once per block, so the binary search costs one global
+// round trip instead of log2(rows) dependent ones.
+constexpr int BIN_SF = 1024;                       // rows whose sub_first fits the shared-memory copy
+__device__ __forceinline__ const uint32_t* stage_sub_first(int gy, const uint32_t* __restrict__ sub_first, uint32_t* s_sf) {
+    if (gy > BIN_SF) return sub_first;
+    for (int i = threadIdx.x; i <= gy; i += blockDim.x) s_sf[i] = __ldg(sub_first + i);
+    __syncthreads();
+    return s_sf;
+}
+__device__ __forceinline__ void locate_sub(uint32_t s, int gy, const uint32_t* sf, const uint32_t* __restrict__ row_start,
+                                           const uint32_t* __restrict__ row_total, int& y, uint32_t& beg, uint32_t& end) {
     int lo = 0, hi = gy;                               // largest y with sub_first[y] <= s
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (__ldg(sub_first + mid) <= s) lo = mid; else hi = mid;
+        if (sf[mid] <= s) lo = mid; else hi = mid;
     }
     y = lo;
     const uint32_t rs = __ldg(row_start + y);
-    beg = rs + (s - __ldg(sub_first + y)) * BIN_CH;
+    beg = rs + (s - sf[y]) * BIN_CH;
     end = min(beg + BIN_CH, rs + __ldg(row_total + y));
-    return true;
 }
 
-// Counting: out[bin] = number of the block's items whose interval covers bin (difference array + prefix sum).
+// Counting: out[bin] = number of the block's items whose interval covers bin: +1 / -1 into a shared difference array
+// (two shared-memory atomics per ITEM), then a prefix sum.
 __device__ __forceinline__ void count_cover(const int (&lo)[BIN_IPT], const int (&hi)[BIN_IPT], int nbins,
                                             uint32_t* __restrict__ out, int* s_diff, uint32_t* s_warp) {
     for (int w0 = 0; w0 < nbins; w0 += BIN_WIN) {
@@ -207,35 +228,45 @@ __device__ __forceinline__ void count_cover(const int (&lo)[BIN_IPT], const int 
 }
 
 // Scatter: the block's items, in order, to out[base(bin) + rank]; rank = number of earlier items of the block that
-// cover the same bin = popcount over the bin's occupancy bitmap (one bit per item).
+// cover the same bin = popcount over the bin's occupancy bitmap (one bit per item, one 32-item word per (bin, batch)).
+//   build    one shared-memory atomicOr per (item, bin).  (Building the words by 32x32 warp bit-transposes of the
+//            items' interval masks instead, fully or for half of the batches, was measured slower: 106 / 91 vs 76 us
+//            for the column scatter of the bench scene — the kernel is issue-bound, not LSU-bound.)
+//   prefix   one thread per bin walks its 32 words: exclusive popcount prefix into a 16-bit table (a warp scan per bin
+//            cost 34 instructions per bin and was 20 % of the kernel, ncu r2k)
+//   emit     one warp per bin, lane = word: every set bit is one output, written at base + prefix + rank-in-word,
+//            so a warp's stores are consecutive.
 template <typename Payload, typename BaseFn>
 __device__ __forceinline__ void scatter_cover(int n_local, const uint32_t* s_lohi, const Payload* s_pay, int nbins,
-                                              uint32_t* s_bits, Payload* __restrict__ out, BaseFn base_of) {
+                                              int win, uint32_t* s_bits, uint16_t* s_pre, uint32_t* s_base,
+                                              Payload* __restrict__ out, BaseFn base_of) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (int w0 = 0; w0 < nbins; w0 += BIN_WIN) {
-        const int wn = min(BIN_WIN, nbins - w0);
+    for (int w0 = 0; w0 < nbins; w0 += win) {                             // win = min(nbins, BIN_BWIN): the shared-memory window
+        const int wn = min(win, nbins - w0);
         for (int i = threadIdx.x; i < wn * BIN_ROW; i += BIN_THREADS) s_bits[i] = 0u;
+        for (int i = threadIdx.x; i < wn; i += BIN_THREADS) s_base[i] = base_of(w0 + i);      // coalesced, one round trip
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < BIN_IPT; k++) {
-            const int j = (int)threadIdx.x + k * BIN_THREADS;
+            const int j = (int)threadIdx.x + k * BIN_THREADS;             // item j: word j >> 5, bit j & 31
             if (j >= n_local) continue;
             const uint32_t lh = s_lohi[j];
             const int a = max((int)(lh & 0xFFFFu), w0), b = min((int)(lh >> 16), w0 + wn);
             for (int bin = a; bin < b; bin++) atomicOr(&s_bits[(bin - w0) * BIN_ROW + (j >> 5)], 1u << (j & 31));
         }
         __syncthreads();
+        for (int i = threadIdx.x; i < wn; i += BIN_THREADS) {
+            uint32_t acc = 0u;
+#pragma unroll 8
+            for (int w = 0; w < BIN_WORDS; w++) {
+                s_pre[i * BIN_PRE + w] = (uint16_t)acc;
+                acc += (uint32_t)__popc(s_bits[i * BIN_ROW + w]);
+            }
+        }
+        __syncthreads();
         for (int r = (int)warp; r < wn; r += BIN_THREADS / 32) {
             uint32_t bits = s_bits[r * BIN_ROW + lane];
-            const uint32_t c = (uint32_t)__popc(bits);
-            uint32_t incl = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= (uint32_t)d) incl += o;
-            }
-            if (__shfl_sync(0xffffffffu, incl, 31) == 0u) continue;       // nobody covers this bin
-            uint32_t pos = base_of(w0 + r) + incl - c;
+            uint32_t pos = s_base[r] + (uint32_t)s_pre[r * BIN_PRE + lane];
             while (bits) {
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1u;
@@ -268,27 +299,34 @@ bin_count_rows_kernel(int n_items, int gy, int band_y0, const uint32_t* __restri
     count_cover(lo, hi, gy, row_count + (size_t)blockIdx.x * gy, s_diff, s_warp);
 }
 
-// rows, step 2: exclusive scan over chunks of every row's counts (one warp per row) -> each (chunk, row)'s base
+// rows, step 2: exclusive scan over chunks of every row's counts -> each (chunk, row)'s base.  One block per tile row;
+// thread t owns a contiguous slice of chunks, so all loads of the block are independent (two memory round trips).
+constexpr int BIN_SCAN_K = 8;                      // chunks per thread and sweep: 256 x 8 = 2048 chunks (2 M Gaussians)
 __global__ void __launch_bounds__(256)
 bin_scan_rows_kernel(int n_chunks, int gy, uint32_t* __restrict__ row_count, uint32_t* __restrict__ row_total)
 {
-    const int y = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    const uint32_t lane = threadIdx.x & 31u;
-    if (y >= gy) return;
-    uint32_t running = 0u;
-    for (int c0 = 0; c0 < n_chunks; c0 += 32) {
-        const int c = c0 + (int)lane;
-        const uint32_t v = c < n_chunks ? row_count[(size_t)c * gy + y] : 0u;
-        uint32_t incl = v;
+    __shared__ uint32_t s_warp[32];
+    const int y = (int)blockIdx.x;
+    uint32_t carry = 0u;
+    for (int c0 = 0; c0 < n_chunks; c0 += 256 * BIN_SCAN_K) {
+        uint32_t v[BIN_SCAN_K], sum = 0u;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += o;
+        for (int k = 0; k < BIN_SCAN_K; k++) {
+            const int c = c0 + (int)threadIdx.x * BIN_SCAN_K + k;
+            v[k] = c < n_chunks ? row_count[(size_t)c * gy + y] : 0u;
+            sum += v[k];
         }
-        if (c < n_chunks) row_count[(size_t)c * gy + y] = running + incl - v;
-        running += __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t tot;
+        uint32_t run = carry + block_scan_excl<256>(sum, s_warp, tot);
+#pragma unroll
+        for (int k = 0; k < BIN_SCAN_K; k++) {
+            const int c = c0 + (int)threadIdx.x * BIN_SCAN_K + k;
+            if (c < n_chunks) row_count[(size_t)c * gy + y] = run;
+            run += v[k];
+        }
+        carry += tot;
     }
-    if (lane == 0) row_total[y] = running;
+    if (threadIdx.x == 0) row_total[y] = carry;
 }
 
 // rows, step 3 (one block): where each row's run list starts, and which column sub-chunks (1024 runs) it is cut into
@@ -319,7 +357,10 @@ bin_scatter_rows_kernel(int n_items, int gy, int band_y0, const uint32_t* __rest
     extern __shared__ __align__(16) uint32_t s_dyn[];
     uint32_t* s_lohi = s_dyn;                                     // y0 | y1 << 16 (band-relative)
     uint2* s_pay = reinterpret_cast<uint2*>(s_dyn + BIN_CH);      // {id, x0 | x1 << 16}
-    uint32_t* s_bits = s_dyn + 3 * BIN_CH;
+    const int win = min(gy, BIN_BWIN);
+    uint32_t* s_base = s_dyn + 3 * BIN_CH;                        // per bin of the window: where this chunk's runs go
+    uint32_t* s_bits = s_dyn + 3 * BIN_CH + win;
+    uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bits + win * BIN_ROW);
     const int base = (int)blockIdx.x * BIN_CH;
     const int n_local = min(BIN_CH, n_items - base);
     for (int j = (int)threadIdx.x; j < BIN_CH; j += BIN_THREADS) {
@@ -337,11 +378,12 @@ bin_scatter_rows_kernel(int n_items, int gy, int band_y0, const uint32_t* __rest
     }
     __syncthreads();
     const uint32_t* my_base = row_base + (size_t)blockIdx.x * gy;
-    scatter_cover<uint2>(n_local, s_lohi, s_pay, gy, s_bits, runs,
+    scatter_cover<uint2>(n_local, s_lohi, s_pay, gy, win, s_bits, s_pre, s_base, runs,
                          [&](int y) { return __ldg(row_start + y) + __ldg(my_base + y); });
 }
 
-// columns, step 1: per (sub-chunk of 1024 runs of one row, tile column) the number of runs covering the tile
+// columns, step 1: per (sub-chunk of 1024 runs of one row, tile column) the number of runs covering the tile.
+// Persistent blocks stride over the sub-chunks (their number is only known on the device).
 __global__ void __launch_bounds__(BIN_THREADS)
 bin_count_cols_kernel(int gy, int gx, const uint32_t* __restrict__ sub_first, const uint32_t* __restrict__ row_start,
                       const uint32_t* __restrict__ row_total, const uint2* __restrict__ runs,
@@ -349,40 +391,52 @@ bin_count_cols_kernel(int gy, int gx, const uint32_t* __restrict__ sub_first, co
 {
     __shared__ int s_diff[BIN_WIN + 1];
     __shared__ uint32_t s_warp[32];
-    int y; uint32_t beg, end;
-    if (!locate_sub(blockIdx.x, gy, sub_first, row_start, row_total, y, beg, end)) return;     // whole block
-    int lo[BIN_IPT], hi[BIN_IPT];
+    __shared__ uint32_t s_sf[BIN_SF + 1];
+    const uint32_t* sf = stage_sub_first(gy, sub_first, s_sf);
+    const uint32_t n_subs = sf[gy];
+    for (uint32_t s = blockIdx.x; s < n_subs; s += gridDim.x) {
+        int y; uint32_t beg, end;
+        locate_sub(s, gy, sf, row_start, row_total, y, beg, end);
+        int lo[BIN_IPT], hi[BIN_IPT];
 #pragma unroll
-    for (int k = 0; k < BIN_IPT; k++) {
-        const uint32_t j = beg + threadIdx.x + (uint32_t)k * BIN_THREADS;
-        lo[k] = hi[k] = 0;
-        if (j < end) {
-            const uint32_t xx = __ldg(&runs[j].y);
-            lo[k] = (int)(xx & 0xFFFFu);
-            hi[k] = (int)(xx >> 16);
+        for (int k = 0; k < BIN_IPT; k++) {
+            const uint32_t j = beg + threadIdx.x + (uint32_t)k * BIN_THREADS;
+            lo[k] = hi[k] = 0;
+            if (j < end) {
+                const uint32_t xx = __ldg(&runs[j].y);
+                lo[k] = (int)(xx & 0xFFFFu);
+                hi[k] = (int)(xx >> 16);
+            }
         }
+        count_cover(lo, hi, gx, col_count + (size_t)s * gx, s_diff, s_warp);
     }
-    count_cover(lo, hi, gx, col_count + (size_t)blockIdx.x * gx, s_diff, s_warp);
 }
 
-// columns, step 2: exclusive scan over the sub-chunks of a row, per tile (one thread per tile); the total is the
-// tile's list length, parked in ranges[tile].y for the scan over tiles
+// columns, step 2: exclusive scan over the sub-chunks of a row, per tile (one warp per tile, lanes over sub-chunks:
+// a row has ~30 at the bench size); the total is the tile's list length, parked in ranges[tile].y for the scan over tiles
 __global__ void __launch_bounds__(256)
 bin_scan_cols_kernel(int gy, int gx, const uint32_t* __restrict__ sub_first, uint32_t* __restrict__ col_count,
                      uint2* __restrict__ ranges)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
     if (t >= (uint32_t)gy * (uint32_t)gx) return;
     const uint32_t y = t / (uint32_t)gx, x = t - y * (uint32_t)gx;
     const uint32_t s0 = __ldg(sub_first + y), s1 = __ldg(sub_first + y + 1);
-    uint32_t acc = 0u;
-    for (uint32_t s = s0; s < s1; s++) {
+    uint32_t running = 0u;
+    for (uint32_t sb = s0; sb < s1; sb += 32u) {
+        const uint32_t s = sb + lane;
         const size_t i = (size_t)s * gx + x;
-        const uint32_t v = col_count[i];
-        col_count[i] = acc;
-        acc += v;
+        const uint32_t v = s < s1 ? col_count[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += o;
+        }
+        if (s < s1) col_count[i] = running + incl - v;
+        running += __shfl_sync(0xffffffffu, incl, 31);
     }
-    ranges[t] = make_uint2(0u, acc);
+    if (lane == 0) ranges[t] = make_uint2(0u, running);
 }
 
 // columns, step 3 (one block): scan over tiles -> ranges[tile] = [start, end) of its list (identifyTileRanges,
@@ -391,20 +445,24 @@ __global__ void __launch_bounds__(1024)
 bin_tile_ranges_kernel(uint32_t tiles, uint2* __restrict__ ranges)
 {
     __shared__ uint32_t s_warp[32];
+    constexpr int K = 16;                              // slabs of 1024 consecutive tiles per sweep (a 2048^2 image = one sweep)
     uint32_t carry = 0u;
-    for (uint32_t t0 = 0; t0 < tiles; t0 += 4096u) {
-        const uint32_t t = t0 + 4u * threadIdx.x;
-        uint32_t c[4];
+    for (uint32_t t0 = 0; t0 < tiles; t0 += 1024u * K) {
+        uint32_t c[K];
 #pragma unroll
-        for (int k = 0; k < 4; k++) c[k] = t + k < tiles ? ranges[t + k].y : 0u;
-        uint32_t tot;
-        uint32_t start = carry + block_scan_excl<1024>(c[0] + c[1] + c[2] + c[3], s_warp, tot);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (t + k < tiles) ranges[t + k] = c[k] ? make_uint2(start, start + c[k]) : make_uint2(0u, 0u);
-            start += c[k];
+        for (int k = 0; k < K; k++) {                  // coalesced, all loads in flight before the first scan
+            const uint32_t t = t0 + 1024u * k + threadIdx.x;
+            c[k] = t < tiles ? ranges[t].y : 0u;
         }
-        carry += tot;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint32_t t = t0 + 1024u * k + threadIdx.x;
+            if (t0 + 1024u * k >= tiles) break;        // uniform
+            uint32_t tot;
+            const uint32_t start = carry + block_scan_excl<1024>(c[k], s_warp, tot);
+            if (t < tiles) ranges[t] = c[k] ? make_uint2(start, start + c[k]) : make_uint2(0u, 0u);
+            carry += tot;
+        }
     }
 }
 
@@ -418,21 +476,29 @@ bin_scatter_cols_kernel(int gy, int gx, const uint32_t* __restrict__ sub_first, 
     extern __shared__ __align__(16) uint32_t s_dyn[];
     uint32_t* s_lohi = s_dyn;                                     // x0 | x1 << 16
     uint32_t* s_pay = s_dyn + BIN_CH;                             // Gaussian id
-    uint32_t* s_bits = s_dyn + 2 * BIN_CH;
-    int y; uint32_t beg, end;
-    if (!locate_sub(blockIdx.x, gy, sub_first, row_start, row_total, y, beg, end)) return;     // whole block
-    const int n_local = (int)(end - beg);
-    for (int j = (int)threadIdx.x; j < BIN_CH; j += BIN_THREADS) {
-        uint2 r = make_uint2(0u, 0u);
-        if (j < n_local) r = __ldg(runs + beg + j);
-        s_pay[j] = r.x;
-        s_lohi[j] = r.y;
+    uint32_t* s_base = s_dyn + 2 * BIN_CH;                        // per tile of the window: where this sub-chunk's ids go
+    const int win = min(gx, BIN_BWIN), nsf = min(gy, BIN_SF) + 1;
+    uint32_t* s_sf = s_dyn + 2 * BIN_CH + win;                    // shared copy of sub_first
+    uint32_t* s_bits = s_dyn + 2 * BIN_CH + win + nsf;
+    uint16_t* s_pre = reinterpret_cast<uint16_t*>(s_bits + win * BIN_ROW);
+    const uint32_t* sf = stage_sub_first(gy, sub_first, s_sf);
+    const uint32_t n_subs = sf[gy];
+    for (uint32_t s = blockIdx.x; s < n_subs; s += gridDim.x) {
+        int y; uint32_t beg, end;
+        locate_sub(s, gy, sf, row_start, row_total, y, beg, end);
+        const int n_local = (int)(end - beg);
+        for (int j = (int)threadIdx.x; j < BIN_CH; j += BIN_THREADS) {
+            uint2 r = make_uint2(0u, 0u);
+            if (j < n_local) r = __ldg(runs + beg + j);
+            s_pay[j] = r.x;
+            s_lohi[j] = r.y;
+        }
+        __syncthreads();
+        const uint32_t* my_base = col_base + (size_t)s * gx;
+        const uint2* row_ranges = ranges + (size_t)y * gx;
+        scatter_cover<uint32_t>(n_local, s_lohi, s_pay, gx, win, s_bits, s_pre, s_base, point_list,
+                                [&](int x) { return __ldg(&row_ranges[x].x) + __ldg(my_base + x); });
     }
-    __syncthreads();
-    const uint32_t* my_base = col_base + (size_t)blockIdx.x * gx;
-    const uint2* row_ranges = ranges + (size_t)y * gx;
-    scatter_cover<uint32_t>(n_local, s_lohi, s_pay, gx, s_bits, point_list,
-                            [&](int x) { return __ldg(&row_ranges[x].x) + __ldg(my_base + x); });
 }
 
 int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, const char* geom,
@@ -466,15 +532,17 @@ int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, c
     const uint32_t n_subs = I / BIN_CH + (uint32_t)gy + 1u;      // >= sum over rows of ceil(runs / 1024)
     if ((size_t)n_chunks > BL.chunk_cap || (size_t)n_subs > BL.sub_cap) { set_error("binning scratch too small"); return -3; }
 
-    const size_t smem_rows = (size_t)(3 * BIN_CH + min(gy, BIN_WIN) * BIN_ROW) * 4;
-    const size_t smem_cols = (size_t)(2 * BIN_CH + min(gx, BIN_WIN) * BIN_ROW) * 4;
-    static_assert((3 * BIN_CH + BIN_WIN * BIN_ROW) * 4 <= 227 * 1024, "bitmap window too large");
+    // item arrays | bases | (sub_first copy) | bitmap window | 16-bit word-prefix table
+    const int win_y = min(gy, BIN_BWIN), win_x = min(gx, BIN_BWIN);
+    const size_t smem_rows = (size_t)(3 * BIN_CH + win_y + win_y * BIN_ROW) * 4 + (size_t)win_y * BIN_PRE * 2;
+    const size_t smem_cols = (size_t)(2 * BIN_CH + win_x + min(gy, BIN_SF) + 1 + win_x * BIN_ROW) * 4 + (size_t)win_x * BIN_PRE * 2;
+    static_assert((3 * BIN_CH + BIN_BWIN + BIN_SF + 1 + BIN_BWIN * BIN_ROW) * 4 + BIN_BWIN * BIN_PRE * 2 <= 100 * 1024, "scatter kernels: > 2 blocks per SM");
     EOGS_CUDA(cudaFuncSetAttribute(bin_scatter_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
     EOGS_CUDA(cudaFuncSetAttribute(bin_scatter_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
 
     bin_count_rows_kernel<<<n_chunks, BIN_THREADS, 0, s>>>(n_items, gy, band.row_begin, order, rect, row_count);
     EOGS_LAUNCH_CHECK("bin_count_rows_kernel");
-    bin_scan_rows_kernel<<<(gy * 32 + 255) / 256, 256, 0, s>>>(n_chunks, gy, row_count, row_total);
+    bin_scan_rows_kernel<<<gy, 256, 0, s>>>(n_chunks, gy, row_count, row_total);
     EOGS_LAUNCH_CHECK("bin_scan_rows_kernel");
     bin_row_offsets_kernel<<<1, 1024, 0, s>>>(gy, row_total, row_start, sub_first);
     EOGS_LAUNCH_CHECK("bin_row_offsets_kernel");
@@ -483,15 +551,22 @@ int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, c
     EOGS_LAUNCH_CHECK("bin_scatter_rows_kernel");
     prof_mark(s, ST_BIN_ROWS);
 
-    bin_count_cols_kernel<<<n_subs, BIN_THREADS, 0, s>>>(gy, gx, sub_first, row_start, row_total, runs, col_count);
+    // the number of sub-chunks is known on the device only (n_subs bounds it): persistent blocks stride over them, as
+    // many as are resident at once (one wave: no late blocks with a full share of the work)
+    int per_sm_count = 0, per_sm_scatter = 0;
+    EOGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_count, bin_count_cols_kernel, BIN_THREADS, 0));
+    EOGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_scatter, bin_scatter_cols_kernel, BIN_THREADS, smem_cols));
+    const uint32_t count_grid = min(n_subs, (uint32_t)(sm_count_cached() * max(per_sm_count, 1)));
+    const uint32_t col_grid = min(n_subs, (uint32_t)(sm_count_cached() * max(per_sm_scatter, 1)));
+    bin_count_cols_kernel<<<count_grid, BIN_THREADS, 0, s>>>(gy, gx, sub_first, row_start, row_total, runs, col_count);
     EOGS_LAUNCH_CHECK("bin_count_cols_kernel");
-    bin_scan_cols_kernel<<<(tiles + 255) / 256, 256, 0, s>>>(gy, gx, sub_first, col_count, ranges);
+    bin_scan_cols_kernel<<<(tiles + 7) / 8, 256, 0, s>>>(gy, gx, sub_first, col_count, ranges);
     EOGS_LAUNCH_CHECK("bin_scan_cols_kernel");
     bin_tile_ranges_kernel<<<1, 1024, 0, s>>>(tiles, ranges);
     EOGS_LAUNCH_CHECK("bin_tile_ranges_kernel");
     prof_mark(s, ST_BIN_COUNT);
 
-    bin_scatter_cols_kernel<<<n_subs, BIN_THREADS, smem_cols, s>>>(gy, gx, sub_first, row_start, row_total, runs, col_count,
+    bin_scatter_cols_kernel<<<col_grid, BIN_THREADS, smem_cols, s>>>(gy, gx, sub_first, row_start, row_total, runs, col_count,
                                                                     ranges, point_list);
     EOGS_LAUNCH_CHECK("bin_scatter_cols_kernel");
     prof_mark(s, ST_BIN_SCATTER);

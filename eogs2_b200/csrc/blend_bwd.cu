@@ -42,6 +42,24 @@
 
 namespace eogs {
 
+#if EOGS_COUNT_PAIRS
+__device__ unsigned long long g_counters_bwd[CNT_COUNT];
+#endif
+int read_counters_bwd(unsigned long long* out, bool reset) {
+#if EOGS_COUNT_PAIRS
+    unsigned long long tmp[CNT_COUNT];
+    EOGS_CUDA(cudaMemcpyFromSymbol(tmp, g_counters_bwd, sizeof(tmp)));
+    for (int i = CNT_BWD_EVAL; i < CNT_BWD_EVAL + 5; i++) out[i] = tmp[i];
+    if (reset) {
+        unsigned long long z[CNT_COUNT] = {};
+        EOGS_CUDA(cudaMemcpyToSymbol(g_counters_bwd, z, sizeof(z)));
+    }
+#else
+    (void)out; (void)reset;
+#endif
+    return 0;
+}
+
 #ifndef EOGS_BWD_WARPS
 #define EOGS_BWD_WARPS 4                     // tiles (= warps) per CTA: 4 = a 2x2 block of tiles, 2 = 2x1, 1 = one tile
 #endif
@@ -143,6 +161,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                              (my_slot >= 2 && my_slot <= 4) ? -0.5f : 1.f;
     const bool slot_takes_op = my_slot >= 2 && my_slot <= 4;
 
+#if EOGS_COUNT_PAIRS
+    unsigned long long cnt_eval = 0ull, cnt_blend = 0ull, cnt_slots = 0ull, cnt_entries = 0ull, cnt_flush = 0ull;   // warp-uniform
+#endif
 #if EOGS_BWD_PERSIST
     const uint32_t n_active = __ldg(sched);                      // tiles with max(n_contrib) > 0, longest first
     for (;;) {
@@ -321,6 +342,11 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     const f2 og2 = mul2(bc2(rb.y), Gv2[r]);
                     a2[r] = mk2(fminf(0.99f, lo2(og2)), fminf(0.99f, hi2(og2)));
                     lane_live |= (v0 || v1) ? (1u << r) : 0u;
+#if EOGS_COUNT_PAIRS
+                    cnt_eval += __popc(__ballot_sync(FULL, pos_e < ncon[2 * r])) + __popc(__ballot_sync(FULL, pos_e < ncon[2 * r + 1]));
+                    cnt_blend += __popc(__ballot_sync(FULL, v0)) + __popc(__ballot_sync(FULL, v1));
+                    cnt_slots += 64ull;
+#endif
                 };
 #if EOGS_BWD_HALF_SKIP
                 const bool top = (me & 0x0Fu) != 0u, bottom = (me & 0xF0u) != 0u;     // warp-uniform
@@ -339,6 +365,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #endif
                 const uint32_t live = __reduce_or_sync(FULL, lane_live);    // bit r: some pixel of strip r accepts (one REDUX)
                 const bool any = live != 0u;
+#if EOGS_COUNT_PAIRS
+                cnt_entries += 1ull; cnt_flush += any ? 1ull : 0ull;
+#endif
 
                 // Stage B: the sequential part (T, accum recurrences).  One 16x4 strip per step = one pixel
                 // PAIR per lane, all arithmetic packed (FFMA2).  Branch-free inside a strip.
@@ -448,6 +477,13 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         cp_async_wait<0>();                    // (the last round committed an empty group)
         __syncwarp();                          // the warp's stages and pixel constants are free for the next tile
     }
+#if EOGS_COUNT_PAIRS
+    if (lane == 0) {
+        atomicAdd(&g_counters_bwd[CNT_BWD_EVAL], cnt_eval); atomicAdd(&g_counters_bwd[CNT_BWD_BLEND], cnt_blend);
+        atomicAdd(&g_counters_bwd[CNT_BWD_SLOTS], cnt_slots); atomicAdd(&g_counters_bwd[CNT_BWD_ENTRIES], cnt_entries);
+        atomicAdd(&g_counters_bwd[CNT_BWD_FLUSHES], cnt_flush);
+    }
+#endif
 }
 
 // Longest-first tile order for the persistent backward (one block; runs right after the forward blend).
@@ -515,18 +551,6 @@ int launch_tile_order(cudaStream_t s, int W, int H, Band band, char* image, cons
     return 0;
 }
 
-static int sm_count() {
-    static thread_local int cached_dev = -1, cached = 0;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (dev != cached_dev) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached = n; cached_dev = dev;
-    }
-    return cached;
-}
-
 int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
                      const GeomLayout& GL, const uint32_t* point_list, const char* image,
                      const ImageLayout& IL, const float* bg, const float* dL_dpix,
@@ -535,7 +559,7 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = band.rows();
 #if EOGS_BWD_PERSIST
     // persistent: as many CTAs as fit on the device at once (4 per SM), never more warps than tiles
-    const int ctas_fit = sm_count() * (16 / BWD_WARPS);
+    const int ctas_fit = sm_count_cached() * (16 / BWD_WARPS);
     const int ctas_need = (tiles_x * tiles_y + BWD_WARPS - 1) / BWD_WARPS;
     const dim3 grid(ctas_need < ctas_fit ? ctas_need : ctas_fit, 1, 1);
 #else

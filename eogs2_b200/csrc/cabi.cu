@@ -120,6 +120,22 @@ EOGS_API int eogs_profile_read(float* ms, int n) {
     return p.n;
 }
 
+// Work counters of the blend kernels since the last reset (pairs_eval, pairs_blend ...).  Returns 1 and
+// fills out[16] (Counter enum of common.cuh) when the library was built with -DEOGS_COUNT_PAIRS=1, 0 (zeros) otherwise.
+// Synchronises the device.
+EOGS_API int eogs_debug_counters(unsigned long long* out, int reset) {
+    for (int i = 0; i < CNT_COUNT; i++) out[i] = 0ull;
+#if EOGS_COUNT_PAIRS
+    EOGS_CUDA(cudaDeviceSynchronize());
+    if (int rc = read_counters_fwd(out, reset != 0)) return rc < 0 ? rc : -rc;
+    if (int rc = read_counters_bwd(out, reset != 0)) return rc < 0 ? rc : -rc;
+    return 1;
+#else
+    (void)reset;
+    return 0;
+#endif
+}
+
 EOGS_API size_t eogs_geom_bytes(int P) { return geom_layout(P).total; }
 EOGS_API size_t eogs_image_bytes(int W, int H) { return image_layout(W, H, full_band(H)).total; }
 EOGS_API size_t eogs_image_bytes_band(int W, int H, int row_begin, int row_end) {
@@ -159,9 +175,14 @@ static int forward_geometry_impl(eogs_stream_t stream, int P, int W, int H, int 
     // set, and only then enqueue the depth sort and the scan.  A host that polls info_host->ready (pinned memory)
     // gets I while those still run and can enqueue the render stage behind them: the GPU never waits for the host
     // round trip (the reference blocks on a cudaMemcpy after its scan, rasterizer_impl.cu:284).
+    // Two stream-ordered copies: the payload (I, error) first, the `ready` word second.  A host that sees `ready` set
+    // therefore reads a complete payload (one 16-byte copy gives no such guarantee: CUDA does not promise that a host
+    // thread observes a device -> host copy atomically or in word order before the stream operation completes).
     EOGS_CUDA(cudaMemsetAsync(&info_dev->ready, 0x01, sizeof(uint32_t), s));
-    if (info_host)
-        EOGS_CUDA(cudaMemcpyAsync(info_host, info_dev, sizeof(eogs_forward_info), cudaMemcpyDeviceToHost, s));
+    if (info_host) {
+        EOGS_CUDA(cudaMemcpyAsync(info_host, info_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        EOGS_CUDA(cudaMemcpyAsync(&info_host->ready, &info_dev->ready, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    }
     if (P > 0) {
         if (int rc = launch_depth_order(s, P, static_cast<char*>(geom), geom_layout(P), info_dev)) return rc;
     }
@@ -274,6 +295,10 @@ EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, i
     if (info_host.error & EOGS_ERR_ALTITUDE_ABOVE_200) {
         set_error("Point is too high: altitude above 200 (reference: __trap, forward.cu:267-272)");
         return -6;
+    }
+    if (info_host.error & EOGS_ERR_TOO_MANY_INSTANCES) {
+        set_error("more than 2^32 (Gaussian, tile) instances: render the view in tile bands (eogs_*_band)");
+        return -3;
     }
     *num_instances = info_host.num_instances;
     void* binning = nullptr;

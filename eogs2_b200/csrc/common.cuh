@@ -73,6 +73,7 @@ struct BinningLayout {       // scratch of the tile-list construction (binning.c
 };
 
 size_t sort_temp_bound(size_t n);
+int sm_count_cached();      // SMs of the current device (148 on B200)
 GeomLayout geom_layout(int P);
 ImageLayout image_layout(int W, int H, Band band);
 Band full_band(int H);
@@ -94,6 +95,20 @@ int cuda_fail(cudaError_t e, const char* what);
         cudaError_t _e = cudaGetLastError();                        \
         if (_e != cudaSuccess) return eogs::cuda_fail(_e, name);    \
     } while (0)
+
+// ---- optional work counters (a separate build: -DEOGS_COUNT_PAIRS=1 -> libeogs_raster_count.so) -----------------
+// The blend kernels count what SURVEY.md section 8d asks every report to carry: evaluated and blended (pixel, Gaussian)
+// pairs, the lane slots spent on them and the list entries walked.  The product library compiles none of it.
+#ifndef EOGS_COUNT_PAIRS
+#define EOGS_COUNT_PAIRS 0
+#endif
+enum Counter : int {
+    CNT_FWD_EVAL = 0, CNT_FWD_BLEND, CNT_FWD_SLOTS, CNT_FWD_ENTRIES,
+    CNT_BWD_EVAL, CNT_BWD_BLEND, CNT_BWD_SLOTS, CNT_BWD_ENTRIES, CNT_BWD_FLUSHES, CNT_COUNT = 16
+};
+// each blend translation unit keeps its own __device__ counters (no relocatable device code) and copies them out
+int read_counters_fwd(unsigned long long* out, bool reset);      // fills out[CNT_FWD_*]
+int read_counters_bwd(unsigned long long* out, bool reset);      // fills out[CNT_BWD_*]
 
 // ---- optional per-stage timing (instrumentation for bench.py; off by default) ----------------
 // When enabled on the calling thread, every stage boundary records a CUDA event on the launch

@@ -168,11 +168,18 @@ preprocess_fwd_kernel(int P, int W, int H, int grid_x, int grid_y, int band_y0, 
     id_in[idx] = (uint32_t)idx;
     // I = sum of tiles touched is published here, by one red.global per warp, instead of after the depth sort and
     // scan: the host needs it to size the binning buffers, and its device -> host copy can then overlap those
-    // two library calls (cabi.cu: forward_geometry_impl).  u32 wrap-around like the reference's scan.
+    // two library calls (cabi.cu: forward_geometry_impl).  The reference's 32-bit scan wraps silently past 2^32
+    // instances; here a wrap raises EOGS_ERR_TOO_MANY_INSTANCES (the host then asks for tile bands) instead of sizing
+    // point_list from a small wrapped count.
     {
         const uint32_t active = __activemask();
-        const uint32_t wsum = __reduce_add_sync(active, out_tiles);
-        if (lane_id() == (uint32_t)(__ffs(active) - 1) && wsum) atomicAdd(&info->num_instances, wsum);
+        const bool huge = out_tiles > 0x03FFFFFFu;                       // keeps the warp sum below 2^31
+        const uint32_t wsum = __reduce_add_sync(active, huge ? 0u : out_tiles);
+        if (huge) atomicOr(&info->error, EOGS_ERR_TOO_MANY_INSTANCES);
+        if (lane_id() == (uint32_t)(__ffs(active) - 1) && wsum) {
+            const uint32_t old = atomicAdd(&info->num_instances, wsum);
+            if (old + wsum < old) atomicOr(&info->error, EOGS_ERR_TOO_MANY_INSTANCES);
+        }
     }
     float4* rec = splat + (size_t)idx * REC_F4;
     rec[0] = r0; rec[1] = r1; rec[2] = r2;

@@ -262,6 +262,13 @@ int launch_preprocess_bwd(cudaStream_t s, int P, int W, int H, int channels, boo
                           float* dL_dmeans3D, float* dL_dcov3D, float* dL_dscales,
                           float* dL_drotations, float* cam_sums)
 {
+    // quaternions travel as float4 (one LDG.128 in, one STG.128 out): a view with a storage offset of an odd number
+    // of floats would fault with "misaligned address" and poison the context — refuse it here instead
+    auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    if ((rotations && !a16(rotations)) || (dL_drotations && !a16(dL_drotations))) {
+        set_error("rotations and dL_drotations must be 16-byte aligned (got %p, %p)", (const void*)rotations, (void*)dL_drotations);
+        return -2;
+    }
     EOGS_CUDA(cudaMemsetAsync(cam_sums, 0, 16 * sizeof(float), s));
     if (raw_params) {
         if (channels != 5 || cov3D_precomp || !alt_affine || !alt_sums) { set_error("the fused-parameter path renders 5 channels from scales+rotations"); return -1; }

@@ -27,6 +27,23 @@ import torch.distributed as dist
 PARAM_ORDER = ("xyz", "f_dc", "opacity", "scaling", "rotation")   # Adam groups, gaussian_model.py:228-259
 
 
+SEGMENT_ALIGN = 4      # floats: every segment of a flat buffer starts on a 16-byte boundary
+
+
+def segment_layout(sizes: Sequence[tuple]) -> tuple:
+    """[(name, numel), ...] -> ({name: (begin, end)}, total).  Segment starts are aligned to 16 bytes, whatever the
+    number of Gaussians: the kernels read quaternions (and write their gradients) as float4, and a rotation segment
+    that starts after 10 * P floats would be misaligned for every odd P (after any prune).  The same rule lays out
+    the gradient bucket (GradBucket) and the optimiser's flat parameter buffer (optim.FlatGaussianAdam), so the
+    all-reduced bucket can be handed to the optimiser step as is."""
+    slices, off = {}, 0
+    for name, k in sizes:
+        off = (off + SEGMENT_ALIGN - 1) // SEGMENT_ALIGN * SEGMENT_ALIGN
+        slices[name] = (off, off + int(k))
+        off += int(k)
+    return slices, off
+
+
 def init_distributed(backend: str | None = None) -> tuple[int, int, int]:
     """Reads RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun); returns (rank, world, local_rank)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -62,16 +79,8 @@ class GradBucket:
     def __post_init__(self):
         self.names = [n for n in PARAM_ORDER if n in self.params] + \
                      sorted(n for n in self.params if n not in PARAM_ORDER)
-        self.slices = {}
-        off = 0
-        for n in self.names:
-            k = self.params[n].numel()
-            self.slices[n] = (off, off + k)
-            off += k
-        for n in sorted(self.extras):
-            k = self.extras[n].numel()
-            self.slices["extra:" + n] = (off, off + k)
-            off += k
+        self.slices, off = segment_layout([(n, self.params[n].numel()) for n in self.names] +
+                                          [("extra:" + n, self.extras[n].numel()) for n in sorted(self.extras)])
         any_p = next(iter(self.params.values()))
         self._exchange, self.exchange_name = None, "ncclAllReduce"
         if self.exchange == "auto" and any_p.is_cuda and dist.is_initialized() and dist.get_world_size() > 1:
@@ -141,6 +150,53 @@ def dp_backward(params: Dict[str, torch.Tensor], cameras: Sequence, render_fn: C
     bucket.all_reduce(average)
     bucket.unpack()
     return total
+
+
+class DensificationStats:
+    """The per-view statistics EOGS++ accumulates between densifications, kept consistent across data-parallel ranks.
+
+    On one GPU the reference updates, after every view (train_pan.py:681-690, scene/gaussian_model.py:719-723):
+
+        max_radii2D[vis]         = max(max_radii2D[vis], radii[vis])
+        xyz_gradient_accum[vis] += || viewspace_points.grad[vis, :2] ||
+        denom[vis]              += 1
+
+    With views sharded over ranks each rank sees only its own views, so replicas that densify on their local statistics
+    diverge (different clone / split decisions -> different Gaussian counts).  `update()` applies the reference's three
+    lines to this rank's LOCAL deltas; `all_reduce()` — one exchange step next to the gradient all-reduce — merges the
+    deltas of all ranks (MAX for the radii, SUM for the two accumulators) into the replicated totals, after which every
+    rank holds exactly what a single GPU would hold after processing the same views (the per-view gradient norms are
+    taken BEFORE any reduction: a norm of summed gradients would be a different statistic).  Only needed when
+    `only_prune=False`."""
+
+    def __init__(self, num_points: int, device):
+        self.max_radii2D = torch.zeros(num_points, device=device)
+        self.xyz_gradient_accum = torch.zeros(num_points, 1, device=device)
+        self.denom = torch.zeros(num_points, 1, device=device)
+        self._d_radii = torch.zeros(num_points, device=device)
+        self._d_sum = torch.zeros(num_points, 2, device=device)          # [gradient-norm sum, view count]
+
+    def update(self, viewspace_point_grad: torch.Tensor, radii: torch.Tensor, visibility_filter: torch.Tensor) -> None:
+        """One rendered view of THIS rank (arguments as in train_pan.py:681-690)."""
+        vis = visibility_filter.reshape(-1)
+        self._d_radii[vis] = torch.max(self._d_radii[vis], radii[vis].to(self._d_radii.dtype))
+        self._d_sum[vis, 0] += torch.norm(viewspace_point_grad[vis, :2], dim=-1)
+        self._d_sum[vis, 1] += 1
+
+    def all_reduce(self, group=None) -> None:
+        """Merge the deltas of all ranks into the replicated totals (2 small collectives: MAX [P], SUM [P, 2])."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self._d_radii, op=dist.ReduceOp.MAX, group=group)
+            dist.all_reduce(self._d_sum, op=dist.ReduceOp.SUM, group=group)
+        self.max_radii2D = torch.max(self.max_radii2D, self._d_radii)
+        self.xyz_gradient_accum += self._d_sum[:, 0:1]
+        self.denom += self._d_sum[:, 1:2]
+        self._d_radii.zero_()
+        self._d_sum.zero_()
+
+    def reset(self, num_points: int) -> None:
+        """After densify_and_prune (densification_postfix, gaussian_model.py:569-571)."""
+        self.__init__(num_points, self.max_radii2D.device)
 
 
 def replicated_adam(params: Dict[str, torch.Tensor], lrs: Dict[str, float]) -> torch.optim.Optimizer:

@@ -26,8 +26,8 @@ from typing import Optional
 import torch
 
 from . import _cabi
-from .rasterizer import (ERR_ALTITUDE_ABOVE_200, ForwardState, GaussianRasterizationSettings, GaussianRasterizer,
-                         _debug_sync, _f32c, _info_host, _ptr, _wait_info, assemble_grad_viewmatrix)
+from .rasterizer import (ERR_ALTITUDE_ABOVE_200, ERR_TOO_MANY_INSTANCES, ForwardState, GaussianRasterizationSettings, GaussianRasterizer,
+                         _debug_sync, _f32c, _info_host, _ptr, _quat16, _wait_info, assemble_grad_viewmatrix)
 
 SH_C0 = 0.28209479177387814        # utils/sh_utils.py:25
 
@@ -56,7 +56,7 @@ def forward_params_raw(bg, xyz, features_dc, opacity_logits, log_scales, raw_rot
         features_dc = _f32c(features_dc.reshape(P, 3), "features_dc", dev)
         opacity_logits = _f32c(opacity_logits, "opacity", dev)
         log_scales = _f32c(log_scales, "scaling", dev)
-        raw_rotations = _f32c(raw_rotations, "rotation", dev)
+        raw_rotations = _quat16(_f32c(raw_rotations, "rotation", dev))
         alt_affine = _f32c(alt_affine, "alt_affine", dev)
         viewmatrix = _f32c(viewmatrix, "viewmatrix", dev)
         bg = _f32c(bg, "bg", dev)
@@ -72,6 +72,9 @@ def forward_params_raw(bg, xyz, features_dc, opacity_logits, log_scales, raw_rot
             _ptr(features_dc), _ptr(alt_affine), _ptr(viewmatrix), float(scale_modifier), int(bool(antialiasing)),
             radii.data_ptr(), geom.data_ptr(), info_dev, info_host.data_ptr()), "eogs_forward_geometry_params_band")
         num_rendered, err = _wait_info(info_np, dev)
+        if err & ERR_TOO_MANY_INSTANCES:
+            raise _cabi.EogsRasterError("more than 2^32 (Gaussian, tile) instances: render the view in tile bands "
+                                        "(eogs2_b200.bands)")
         if err & ERR_ALTITUDE_ABOVE_200:
             raise RuntimeError("Point is too high: a Gaussian's altitude exceeds 200 (depth = 200 - altitude < 0)")
         _debug_sync(debug, "preprocess")
@@ -110,7 +113,7 @@ def backward_params_raw(state: ForwardState, bg, xyz, opacity_logits, log_scales
         xyz = _f32c(xyz, "xyz", dev)
         opacity_logits = _f32c(opacity_logits, "opacity", dev)
         log_scales = _f32c(log_scales, "scaling", dev)
-        raw_rotations = _f32c(raw_rotations, "rotation", dev)
+        raw_rotations = _quat16(_f32c(raw_rotations, "rotation", dev))
         alt_affine = _f32c(alt_affine, "alt_affine", dev)
         viewmatrix = _f32c(viewmatrix, "viewmatrix", dev)
         projmatrix = _f32c(projmatrix, "projmatrix", dev)

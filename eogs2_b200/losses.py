@@ -58,9 +58,11 @@ class _Photometric(torch.autograd.Function):
                 float(lambda_dssim), maps.data_ptr(), scal.data_ptr(), scal[2:].data_ptr()), "eogs_photometric_forward")
         ctx.save_for_backward(img, ref, maps)
         ctx.lambda_dssim = float(lambda_dssim)
-        out = scal[2:]
-        ctx.mark_non_differentiable(out[1:])
-        return out[0], out[1].detach(), out[2].detach()
+        # the very tensor objects that are returned must be the ones marked: a view made afterwards would be a fresh
+        # output that autograd attaches a grad_fn to (and whose incoming gradient backward() would silently drop)
+        loss, ssim_mean, l1_mean = scal[2], scal[3], scal[4]
+        ctx.mark_non_differentiable(ssim_mean, l1_mean)
+        return loss, ssim_mean, l1_mean
 
     @staticmethod
     def backward(ctx, g_loss, _g_ssim, _g_l1):

@@ -23,7 +23,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _cabi
-from .dp import PARAM_ORDER
+from .dp import PARAM_ORDER, segment_layout
 
 
 class FlatGaussianAdam:
@@ -48,10 +48,8 @@ class FlatGaussianAdam:
 
     # ---- layout ---------------------------------------------------------------------------------
     def _alloc(self, P: int) -> None:
-        self.slices, off = {}, 0
-        for n in self.names:
-            self.slices[n] = (off, off + P * self.width[n])
-            off += P * self.width[n]
+        # 16-byte aligned segment starts for ANY P (dp.segment_layout): the rasterizer reads the rotation view as float4
+        self.slices, off = segment_layout([(n, P * self.width[n]) for n in self.names])
         self.numel = off
         with torch.cuda.device(self.device):
             self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
@@ -69,6 +67,16 @@ class FlatGaussianAdam:
         """e.g. the exponential xyz schedule (update_learning_rate, scene/gaussian_model.py:273-279)."""
         self.lrs[name] = float(lr)
 
+    def pack(self, tensors: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """{name: per-parameter tensor} -> one flat fp32 tensor in this optimiser's (16-byte aligned) segment layout,
+        e.g. gradients to hand to step(flat_grads=...).  Segments that are absent stay zero."""
+        with torch.cuda.device(self.device):
+            out = torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+        for n, t in tensors.items():
+            a, b = self.slices[n]
+            out[a:b].copy_(t.reshape(-1))
+        return out
+
     def zero_grad(self) -> None:
         for p in self.params.values():
             p.grad = None
@@ -76,7 +84,10 @@ class FlatGaussianAdam:
     # ---- step -----------------------------------------------------------------------------------
     def step(self, flat_grads: Optional[torch.Tensor] = None) -> None:
         """One Adam step of every group.  flat_grads: a [numel] fp32 tensor in this layout (the all-reduced
-        bucket of dp.GradBucket); by default the views' .grad are packed (missing grads count as zero)."""
+        bucket of dp.GradBucket); by default the views' .grad are packed.  A view whose .grad is None is stepped with a
+        ZERO gradient (its moments decay and it keeps moving along them) — torch.optim.Adam, which the reference uses,
+        skips such a parameter entirely; the rasterizer's backward always produces every gradient, so the two only
+        differ for segments the caller never renders."""
         lib = _cabi.load()
         if self.numel == 0:
             return
@@ -92,7 +103,9 @@ class FlatGaussianAdam:
             raise _cabi.EogsRasterError("flat_grads must be a contiguous float32 tensor covering the parameter layout")
         self.t += 1
         k = len(self.names)
-        ends = (C.c_ulonglong * k)(*[self.slices[n][1] for n in self.names])
+        # a segment ends where the next one begins: the (zero-gradient, zero-valued) alignment padding rides along
+        starts = [self.slices[n][0] for n in self.names]
+        ends = (C.c_ulonglong * k)(*(starts[1:] + [self.numel]))
         lrs = (C.c_float * k)(*[self.lrs[n] for n in self.names])
         with torch.cuda.device(self.device), torch.no_grad():
             _cabi.check(lib.eogs_adam_step(

@@ -17,6 +17,8 @@ on a CUDA device and the shared library must be present.
 from __future__ import annotations
 
 import ctypes as C
+import threading
+import time
 from dataclasses import dataclass
 from typing import NamedTuple, Optional
 
@@ -27,6 +29,7 @@ from . import _cabi
 
 NUM_CHANNELS = 5          # DGR/cuda_rasterizer/config.h:14
 ERR_ALTITUDE_ABOVE_200 = 1
+ERR_TOO_MANY_INSTANCES = 2
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -77,8 +80,14 @@ class ForwardState:
 _pinned_info: dict = {}
 
 
+def _info_key(device: torch.device):
+    # one pinned slot per (device, stream, host thread): two Python threads rendering on the same stream must not
+    # share the words a device -> host copy is about to fill
+    return (device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+
+
 def _info_host(device: torch.device) -> torch.Tensor:
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    key = _info_key(device)
     t = _pinned_info.get(key)
     if t is None:
         buf = torch.zeros(4, dtype=torch.int32).pin_memory()        # eogs_forward_info: I, error, ready, reserved
@@ -93,20 +102,24 @@ def _info_host(device: torch.device) -> torch.Tensor:
     return t[0], t[1]
 
 
+_POLL_SECONDS = 2e-3
+
+
 def _wait_info(info_np, device: torch.device):
-    """Wait for the geometry stage's (I, error) words.  Their copy into pinned memory is enqueued right after the
-    projection kernel, before the depth sort and the scan, so polling the `ready` word returns while those still
-    run and the render stage can be enqueued behind them without a GPU bubble (the reference blocks on a
-    cudaMemcpy after its scan, rasterizer_impl.cu:284).  Bounded: after a few hundred microseconds of polling it
-    falls back to a stream synchronisation, which also surfaces CUDA errors."""
-    for _ in range(4000):
-        if info_np[2] != 0:
+    """Wait for the geometry stage's (I, error) words.  Their copies into pinned memory are enqueued right after the
+    projection kernel, before the depth sort — payload first, then the `ready` word (cabi.cu) — so polling `ready`
+    returns while the sort still runs and the render stage can be enqueued behind it without a GPU bubble (the
+    reference blocks on a cudaMemcpy after its scan, rasterizer_impl.cu:284).  The payload is read only AFTER `ready`
+    was seen.  Time-bounded: after 2 ms of polling it falls back to a stream synchronisation, which also surfaces
+    CUDA errors."""
+    deadline = time.perf_counter() + _POLL_SECONDS
+    while info_np[2] == 0:
+        if time.perf_counter() > deadline:
+            torch.cuda.current_stream(device).synchronize()
+            if info_np[2] == 0:
+                raise _cabi.EogsRasterError("geometry stage finished without publishing its instance count")
             break
-    else:
-        torch.cuda.current_stream(device).synchronize()
-        if info_np[2] == 0:
-            raise _cabi.EogsRasterError("geometry stage finished without publishing its instance count")
-    entry = _pinned_info.get((device.index, torch.cuda.current_stream(device).cuda_stream))
+    entry = _pinned_info.get(_info_key(device))
     if entry is not None:
         entry[2] = False                   # collected
     return int(info_np[0]) & 0xFFFFFFFF, int(info_np[1])
@@ -126,6 +139,12 @@ def _f32c(t: torch.Tensor, name: str, device: torch.device) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise _cabi.EogsRasterError(f"{name} must be float32, got {t.dtype}")
     return t.contiguous()
+
+
+def _quat16(t: torch.Tensor) -> torch.Tensor:
+    """Quaternions are read as float4: a view whose storage offset leaves it only 4-byte aligned (legal input for the
+    reference, which indexes floats) is copied once into an aligned buffer."""
+    return t if t.numel() == 0 or t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
 
 
 def _debug_sync(debug: bool, what: str) -> None:
@@ -178,7 +197,7 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         colors = _f32c(colors, "colors_precomp", dev)
         opacities = _f32c(opacities, "opacities", dev)
         scales = _f32c(scales, "scales", dev)
-        rotations = _f32c(rotations, "rotations", dev)
+        rotations = _quat16(_f32c(rotations, "rotations", dev))
         cov3D_precomp = _f32c(cov3D_precomp, "cov3D_precomp", dev)
         viewmatrix = _f32c(viewmatrix, "viewmatrix", dev)
         bg = _f32c(bg, "bg", dev)
@@ -200,6 +219,9 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         # The instance count sizes the binning buffers (reference: blocking cudaMemcpy,
         # rasterizer_impl.cu:284).
         num_rendered, err = _wait_info(info_np, dev)
+        if err & ERR_TOO_MANY_INSTANCES:
+            raise _cabi.EogsRasterError("more than 2^32 (Gaussian, tile) instances: render the view in tile bands "
+                                        "(eogs2_b200.bands)")
         if err & ERR_ALTITUDE_ABOVE_200:
             # reference: device printf("Point is too high") + __trap() (forward.cu:267-272)
             raise RuntimeError("Point is too high: a Gaussian's altitude exceeds 200 (depth = 200 - altitude < 0)")
@@ -244,6 +266,9 @@ def rasterize_backward_raw(state: ForwardState, bg, means3D, colors, opacities, 
             if (t.device != dev or t.dtype != torch.float32 or not t.is_contiguous()
                     or t.numel() != int(torch.Size(shape).numel())):
                 raise _cabi.EogsRasterError(f"out[{key!r}] must be a contiguous float32 tensor of shape {tuple(shape)} on {dev}")
+            if key == "rotations" and t.numel() and t.data_ptr() % 16 != 0:
+                raise _cabi.EogsRasterError("out['rotations'] must be 16-byte aligned (quaternion gradients are stored as float4): "
+                                            "start the segment on a multiple of 4 floats (dp.segment_layout)")
             return t.view(shape)
 
         dL_dmeans2D = buf("means2D", (P, 3))
@@ -263,7 +288,7 @@ def rasterize_backward_raw(state: ForwardState, bg, means3D, colors, opacities, 
         colors = _f32c(colors, "colors_precomp", dev)
         opacities = _f32c(opacities, "opacities", dev)
         scales = _f32c(scales, "scales", dev)
-        rotations = _f32c(rotations, "rotations", dev)
+        rotations = _quat16(_f32c(rotations, "rotations", dev))
         cov3D_precomp = _f32c(cov3D_precomp, "cov3D_precomp", dev)
         viewmatrix = _f32c(viewmatrix, "viewmatrix", dev)
         projmatrix = _f32c(projmatrix, "projmatrix", dev)

@@ -57,6 +57,8 @@ extern "C" {
 
 /* error bits reported in eogs_forward_info.error */
 #define EOGS_ERR_ALTITUDE_ABOVE_200 1u  /* reference: printf + __trap(), forward.cu:267-272 */
+#define EOGS_ERR_TOO_MANY_INSTANCES 2u  /* sum of tiles touched wrapped 32 bits (the reference's scan wraps silently,
+                                           rasterizer_impl.cu:280-284): render the view in tile bands */
 
 typedef void* eogs_stream_t;    /* cudaStream_t */
 
@@ -73,6 +75,11 @@ typedef struct eogs_forward_info {
 
 EOGS_API int eogs_abi_version(void);
 EOGS_API const char* eogs_last_error(void);
+
+/* Instrumentation (developer builds): work counters of the blend kernels — evaluated / blended (pixel, Gaussian)
+ * pairs, lane slots, list entries — since the last reset.  out[16]; returns 1 when the library
+ * was compiled with -DEOGS_COUNT_PAIRS=1 (libeogs_raster_count.so), 0 and zeros for the product library. */
+EOGS_API int eogs_debug_counters(unsigned long long* out, int reset);
 
 /* ---- scratch sizing (host only, no CUDA calls that touch a device) ---------------- */
 /* Per-Gaussian state kept from forward to backward (packed splat records, depths, tile

@@ -21,7 +21,12 @@ def _rows(x, P=None):
     return x.reshape(x.shape[0] if P is None else P, -1)
 
 
-def violations(a, b, rtol=1e-3, atol_frac=1e-6):
+# absolute floor as a fraction of max|ref|: float accumulation noise of the sums (measured need: 1e-7 for the blend-level
+# gradients, 3e-6 for dL_dscales / dL_drotations whose chain through the inverse 2D covariance amplifies it)
+ATOL_FRAC = 2e-5
+
+
+def violations(a, b, rtol=1e-3, atol_frac=ATOL_FRAC):
     """Per-element excess over the bar, reduced per Gaussian.  Returns (rows violating, worst excess / max|b|, rows)."""
     a, b = _rows(a), _rows(b)
     absmax = np.abs(b).max() if b.size else 0.0
@@ -32,7 +37,7 @@ def violations(a, b, rtol=1e-3, atol_frac=1e-6):
     return len(bad), max(worst, 0.0), bad
 
 
-def assert_grad_close(a, b, what, rtol=1e-3, atol_frac=1e-6, allow_rows=0):
+def assert_grad_close(a, b, what, rtol=1e-3, atol_frac=ATOL_FRAC, allow_rows=0):
     """Every Gaussian within the bar, except `allow_rows` (Gaussians that own a pixel whose accept decision flipped
     between two exp implementations; 0 when both sides use the same one)."""
     n, worst, bad = violations(a, b, rtol, atol_frac)
@@ -40,7 +45,7 @@ def assert_grad_close(a, b, what, rtol=1e-3, atol_frac=1e-6, allow_rows=0):
                             f"{worst:.2e} x max|ref|; first rows {bad[:8].tolist()}"
 
 
-def assert_no_worse_than_rerun(ours, ref, ref_rerun, what, rtol=1e-3, atol_frac=1e-6, factor=3.0, slack_rows=2):
+def assert_no_worse_than_rerun(ours, ref, ref_rerun, what, rtol=1e-3, atol_frac=ATOL_FRAC, factor=3.0, slack_rows=2):
     """Against a reference whose own atomics make it non-deterministic: our violations of the bar must be explained
     by the reference's run-to-run noise — no more violating Gaussians than `factor` x (what the reference shows against
     itself) + slack, and no worse excess."""

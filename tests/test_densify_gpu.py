@@ -70,7 +70,7 @@ def test_densify_and_prune_matches_reference(cuda_dev, P, max_screen_size, seed)
     flat = O.FlatGaussianAdam(init, LRS)
     for it in range(2):                                     # non-trivial moments
         gr = grads_like(dev, init, 50 + it, 1e-3)
-        flat.step(torch.cat([gr[n].reshape(-1) for n in flat.names]))
+        flat.step(flat.pack(gr))
     p = {n: flat.params[n].detach().clone() for n in flat.names}
     m = {n: flat.exp_avg[slice(*flat.slices[n])].view_as(p[n]).clone() for n in flat.names}
     v = {n: flat.exp_avg_sq[slice(*flat.slices[n])].view_as(p[n]).clone() for n in flat.names}

@@ -78,12 +78,58 @@ def test_two_rank_step_equals_single_process_accumulation(tmp_path):
     r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
     g_ref, p_ref = single_process_reference()
     assert r0["shard"] == [0, 2, 4] and r1["shard"] == [1, 3]
-    assert r0["bucket_numel"] == 257 * 14 + 16           # 14 floats per Gaussian + the camera extras
+    # 14 floats per Gaussian + the camera extras, every segment starting on a 16-byte boundary (odd P: 6 floats of padding)
+    sizes = [("xyz", 771), ("f_dc", 771), ("opacity", 257), ("scaling", 771), ("rotation", 1028), ("extra:cam0", 16)]
+    slices, total = dp.segment_layout(sizes)
+    assert r0["bucket_numel"] == total == 257 * 14 + 16 + 6 and all(a % 4 == 0 for a, _ in slices.values())
     for n in g_ref:
         assert torch.allclose(r0["grads0"][n], g_ref[n], rtol=1e-5, atol=1e-7), n
         assert torch.equal(r0["grads0"][n], r1["grads0"][n]), n         # identical on every rank
         assert torch.equal(r0["params"][n], r1["params"][n]), n         # replicas never drift
         assert torch.allclose(r0["params"][n], p_ref[n], rtol=1e-4, atol=1e-6), n
+
+
+def stats_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = dp.init_distributed("gloo")
+    P, views = 101, stats_views()
+    st = dp.DensificationStats(P, "cpu")
+    for it in range(2):                                   # two iterations between densifications
+        for i in dp.shard_views(len(views), r, w):
+            st.update(*views[i])
+        st.all_reduce()
+    torch.save({"max_radii2D": st.max_radii2D, "accum": st.xyz_gradient_accum, "denom": st.denom}, out + f".{rank}")
+    dist.destroy_process_group()
+
+
+def stats_views(P=101, n=5):
+    g = torch.Generator().manual_seed(3)
+    views = []
+    for _ in range(n):
+        radii = torch.randint(0, 30, (P,), generator=g).int() * (torch.rand(P, generator=g) < 0.7)
+        views.append((torch.randn(P, 3, generator=g), radii, (radii > 0).nonzero()))
+    return views
+
+
+def test_densification_statistics_match_a_single_gpu_run(tmp_path):
+    """max_radii2D (MAX) and xyz_gradient_accum / denom (SUM) after a 2-rank run equal the reference's single-GPU
+    bookkeeping over the same views (train_pan.py:681-690, gaussian_model.py:719-723), on every rank."""
+    out = str(tmp_path / "stats")
+    mp.spawn(stats_worker, args=(2, free_port(), out), nprocs=2, join=True)
+    r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    P, views = 101, stats_views()
+    max_radii2D, accum, denom = torch.zeros(P), torch.zeros(P, 1), torch.zeros(P, 1)
+    for it in range(2):
+        for grad, radii, vis in views:                    # the reference's three lines, view after view
+            v = vis.reshape(-1)
+            max_radii2D[v] = torch.max(max_radii2D[v], radii[v].float())
+            accum[v] += torch.norm(grad[v, :2], dim=-1, keepdim=True)
+            denom[v] += 1
+    for r in (r0, r1):
+        assert torch.equal(r["max_radii2D"], max_radii2D) and torch.equal(r["denom"], denom)
+        assert torch.allclose(r["accum"], accum, rtol=1e-6, atol=1e-7)
+    assert torch.equal(r0["accum"], r1["accum"])          # replicas hold identical statistics
 
 
 def test_shard_views_partition():

@@ -58,3 +58,61 @@ def test_fused_iteration_matches_the_torch_iteration_and_trains(cuda_dev):
     assert losses_f[-1] < losses_f[0]
     for n in ref_p:
         assert rel(opt.params[n], ref_p[n]) < 1e-4, n
+
+
+def test_odd_gaussian_counts_after_prune_keep_every_view_aligned(cuda_dev):
+    """After prune() the number of Gaussians is arbitrary.  The flat layout (dp.segment_layout) starts every segment
+    on a 16-byte boundary, so the rotation view the geometry kernel loads as float4 stays aligned for odd P, and the
+    composed iteration keeps running (it raised 'rotations must be 16-byte aligned' for every odd P before)."""
+    dev, P, W, H = cuda_dev, 10_001, 128, 96
+    pipe = SimpleNamespace(debug=False, antialiasing=False, compute_cov3D_python=False, require_radii=False)
+    bg = S.background(4).to(dev)
+    cam, sun, cam2sun = R.make_cameras(dev, 4, W, H)
+    opt = O.FlatGaussianAdam(R.raw_params(dev, P, 4), LRS)
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
+    for keep_every in (None, 3):                       # P = 10 001 (odd), then 6 667 survivors (odd)
+        if keep_every:
+            keep = torch.ones(opt.P, dtype=torch.bool, device=dev)
+            keep[::keep_every] = False
+            opt.prune(keep)
+        assert opt.P % 2 == 1
+        for n in opt.names:
+            assert opt.params[n].data_ptr() % 16 == 0, (n, opt.P)
+        opt.zero_grad()
+        loss, _ = IT.camera_iteration(cam, sun, cam2sun, IT.model_view(opt.params), pipe, bg, gt)
+        loss.backward()
+        assert all(torch.isfinite(opt.params[n].grad).all() for n in opt.names)
+        opt.step()
+
+
+def test_misaligned_quaternion_views_are_handled_not_faulted(cuda_dev):
+    """A rotations INPUT view with an odd storage offset is legal for the reference (it indexes floats): it is copied
+    into an aligned buffer.  A misaligned rotations OUTPUT buffer (out=) is refused with a Python error instead of a
+    'misaligned address' fault that would poison the CUDA context."""
+    import eogs2_b200 as E
+    from eogs2_b200._cabi import EogsRasterError
+    dev, P, W, H = cuda_dev, 2001, 96, 80
+    sc = S.make_scene(P, "trained", 8).to(dev)
+    view = S.make_camera(8).to(dev)
+    colors = S.colors_precomp(S.make_scene(P, "trained", 8), S.make_camera(8)).to(dev)
+    bg = S.background(8).to(dev)
+    empty = torch.empty(0, device=dev)
+    store = torch.zeros(4 * P + 1, device=dev)
+    rot_view = store[1:].view(P, 4)                    # 4-byte aligned only
+    rot_view.copy_(sc.rotations)
+    assert rot_view.data_ptr() % 16 != 0
+    st_a = E.rasterize_forward_raw(bg, sc.means3D, colors, sc.opacities, sc.scales, sc.rotations, 1.0, empty, view, H, W)
+    st_b = E.rasterize_forward_raw(bg, sc.means3D, colors, sc.opacities, sc.scales, rot_view, 1.0, empty, view, H, W)
+    assert torch.equal(st_a.color, st_b.color)
+    dcol, dinv = (t.to(dev) for t in S.upstream_grads(5, H, W, 8, True))
+    g_ref = E.rasterize_backward_raw(st_b, bg, sc.means3D, colors, sc.opacities, sc.scales, rot_view, 1.0, empty, view, view,
+                                     dcol, dinv)
+    bad = torch.zeros(4 * P + 1, device=dev)[1:].view(P, 4)
+    with pytest.raises(EogsRasterError, match="16-byte aligned"):
+        E.rasterize_backward_raw(st_b, bg, sc.means3D, colors, sc.opacities, sc.scales, rot_view, 1.0, empty, view, view,
+                                 dcol, dinv, out={"rotations": bad})
+    good = torch.zeros(P, 4, device=dev)
+    g = E.rasterize_backward_raw(st_b, bg, sc.means3D, colors, sc.opacities, sc.scales, rot_view, 1.0, empty, view, view,
+                                 dcol, dinv, out={"rotations": good})
+    torch.cuda.synchronize()                            # the context is still healthy
+    assert g[6].data_ptr() == good.data_ptr() and rel(g[6], g_ref[6]) < 1e-5

@@ -56,6 +56,7 @@ def test_photometric_loss_matches_torch(cuda_dev, C, H, W, lam, seed):
         loss_ref = ref_photometric(a, gt, lam)
         (loss_ref * up).backward()
     loss, ssim_mean, l1_mean = L.photometric_loss(b, gt, lam, return_parts=True)
+    assert loss.requires_grad and not ssim_mean.requires_grad and not l1_mean.requires_grad     # logged values are detached
     (loss * up).backward()
     assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-5 * max(1.0, abs(float(loss_ref.detach())))
     assert abs(float(l1_mean) - float(torch.abs(base - gt).mean())) <= 1e-6

@@ -52,7 +52,7 @@ def test_flat_adam_matches_torch_adam_and_pruning(cuda_dev):
                 flat.params[n].grad = gr[n].clone()
             flat.step()
         else:                                              # ... or as one flat bucket (the all-reduced DP buffer)
-            flat.step(torch.cat([gr[n].reshape(-1) for n in flat.names]))
+            flat.step(flat.pack(gr))
         for n in ref_p:
             assert close(flat.params[n], ref_p[n], 2e-6), (it, n)
 

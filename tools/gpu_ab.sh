@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
 tail -8 $OUT/pytest_gpu.log
 leg() {  # name, env
-  env $2 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > $OUT/bench_$1.json 2> $OUT/bench_$1.err
+  env $2 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e --no-config5 > $OUT/bench_$1.json 2> $OUT/bench_$1.err
   python - <<PY
 import json
 try:

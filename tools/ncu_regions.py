@@ -5,7 +5,15 @@ import sys
 from collections import Counter
 
 rows = list(csv.reader(open(sys.argv[1])))
-hdr, data = rows[1], rows[2:]
+# several kernels in one export: sections start with a "Kernel Name" row; take the first (or the one whose name contains argv[3])
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+pick = 0
+if len(sys.argv) > 3:
+    pick = next((k for k, i in enumerate(starts) if sys.argv[3] in rows[i][1]), 0)
+lo = starts[pick]
+hi = starts[pick + 1] if pick + 1 < len(starts) else len(rows)
+print(rows[lo][1][:100])
+hdr, data = rows[lo + 1], [r for r in rows[lo + 2:hi] if len(r) > 5]
 ix = {h: i for i, h in enumerate(hdr)}
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 2.0
 tot_s = sum(int(r[ix['# Samples']] or 0) for r in data)
