@@ -70,6 +70,50 @@ __device__ __forceinline__ uint32_t patch_mask(const float4& r0, const float4& r
     return m;
 }
 
+// 4-bit mask of the 8x8 REGIONS of a tile (bit 2R + c: rows 8R..8R+7, columns 8c..8c+7) the Gaussian may contribute
+// to — the forward kernel's granularity (one warp per region).  Same exact test as patch_mask with two row bands of 8
+// pixels instead of four of 4: three square roots instead of five, and by construction equal to OR-ing the two patch
+// bits of each region (an ellipse meets a union of boxes iff it meets one of them).
+__device__ __forceinline__ uint32_t region_mask(const float4& r0, const float4& r1, float tx0, float ty0,
+                                                float img_x1, float img_y1) {
+    constexpr int ROWS = 2, COLS = 2, RH = 8, RW = 8;
+    const float mx = r0.x, my = r0.y, A = r0.z, B = r0.w, C = r1.x, op = r1.y;
+    const float qmax = 2.f * __logf(255.f * op) + 0.1f;
+    if (qmax <= 0.f) return 0u;
+    const float det = A * C - B * B;
+    const float inv_det = __fdividef(1.f, det), invA = __fdividef(1.f, A);
+    const float hx = __fsqrt_rn(qmax * C * inv_det), hy = __fsqrt_rn(qmax * A * inv_det);
+    if (mx + hx < tx0 || mx - hx > tx0 + (TILE - 1) || my + hy < ty0 || my - hy > ty0 + (TILE - 1)) return 0u;
+    const float slope = -B * invA;
+    const float dy_right = __fdividef(-B * hx, C), dy_left = -dy_right;
+    const float Aq = A * qmax;
+    float dyl[ROWS + 1], xr[ROWS + 1], xl[ROWS + 1];
+#pragma unroll
+    for (int k = 0; k <= ROWS; k++) {
+        dyl[k] = (ty0 + (float)(RH * k) - 0.5f) - my;
+        const float dyc = fminf(fmaxf(dyl[k], -hy), hy);
+        const float h = __fsqrt_rn(fmaxf(0.f, Aq - det * dyc * dyc)) * invA;
+        const float c = mx + slope * dyc;
+        xr[k] = c + h;
+        xl[k] = c - h;
+    }
+    uint32_t m = 0u;
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        if (dyl[r + 1] < -hy || dyl[r] > hy) continue;
+        if (ty0 + (float)(RH * r) > img_y1) continue;
+        const float right = (dy_right > dyl[r] && dy_right < dyl[r + 1]) ? mx + hx : fmaxf(xr[r], xr[r + 1]);
+        const float left = (dy_left > dyl[r] && dy_left < dyl[r + 1]) ? mx - hx : fminf(xl[r], xl[r + 1]);
+#pragma unroll
+        for (int c = 0; c < COLS; c++) {
+            const float px0 = tx0 + (float)(RW * c);
+            if (px0 > img_x1) continue;
+            if (!(right < px0 - 0.01f || left > px0 + (RW - 1) + 0.01f)) m |= 1u << (r * COLS + c);
+        }
+    }
+    return m;
+}
+
 // ---- warp reduction of the backward's per-pair terms ------------------------------------------
 // Transposing butterfly level: N live values -> ceil(N/2), partner = lane ^ (1 << BIT).
 template <int N, int BIT>

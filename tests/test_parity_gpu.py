@@ -282,3 +282,89 @@ def test_full_size_gradient_consistency(cuda_dev, full_case):
     rhs = (d_colors.double() * v.double()).sum()
     scale = float((d_colors.double() * v.double()).abs().sum())
     assert abs(float(lhs - rhs)) <= 1e-3 * scale
+
+
+# ------------------------------------------------------------------------------------------------
+# adversarial scenes aimed at the exact patch culling (csrc/blend_common.cuh: patch_mask) and at alpha_cut
+def adversarial_case(W, H, seed, n_each=1500):
+    """Gaussians built in PIXEL space (mapped back through the inverse camera) to sit where a conservative-but-wrong
+    culling test would fail: needles with anisotropy up to 1e4 crossing patch corners, near-singular conics,
+    opacities within a few ulps of 1/255 (centre alpha on the accept threshold), centres exactly on patch / tile
+    boundaries and half-pixel positions, footprints much larger than the image with barely visible opacity."""
+    g = torch.Generator().manual_seed(seed)
+    u = lambda *s: torch.rand(*s, generator=g)
+    view = S.make_camera(seed)
+    M = view.t()
+    A, b = M[:3, :3].double(), M[:3, 3].double()
+    groups = []
+
+    def place(px, py, alt):
+        ndc = torch.stack([(2 * px + 1) / W - 1, (2 * py + 1) / H - 1, alt], 1).double()
+        return ((ndc - b) @ torch.linalg.inv(A).t()).float()
+
+    n = n_each
+    bx = (torch.randint(0, W // 8 + 1, (n,), generator=g) * 8).float()           # patch boundaries in x (every 8 px)
+    by = (torch.randint(0, H // 4 + 1, (n,), generator=g) * 4).float()           # patch boundaries in y (every 4 px)
+    half = torch.where(u(n) < 0.5, torch.full((n,), -0.5), torch.zeros(n))
+    alt = -20 + 80 * u(n)
+    # 1. needles: one long axis, one tiny axis, random in-plane rotation, centres on patch corners
+    big = 10 ** (-2.3 + 1.3 * u(n)); small = big * 10 ** (-4 * u(n))
+    groups.append((place(bx + half, by + half, alt), torch.stack([big, small, small], 1), None, 0.05 + 0.9 * u(n, 1)))
+    # 2. opacity on the accept threshold: 1/255 and its float neighbours, small round splats on pixel centres / corners
+    thr = torch.tensor(1.0 / 255.0)
+    ulps = torch.randint(-3, 12, (n,), generator=g).to(torch.int32)
+    op = (thr.view(torch.int32) + ulps).view(torch.float32).reshape(n, 1)
+    s2 = (10 ** (-3.2 + 0.8 * u(n, 1))).repeat(1, 3)
+    groups.append((place(u(n) * W - 0.5 * (u(n) < 0.5), u(n) * H, alt), s2, None, op))
+    # 3. near-singular 3D covariances (two tiny axes) seen edge-on and face-on
+    tiny = 10 ** (-6 + 1.5 * u(n))
+    groups.append((place(u(n) * W, u(n) * H, alt), torch.stack([10 ** (-2.5 + u(n)), tiny, tiny * 10 ** (-u(n))], 1), None,
+                   0.3 + 0.69 * u(n, 1)))
+    # 4. huge footprints with barely visible opacity, and centres far outside the image reaching in
+    groups.append((place(W * (u(n) * 3 - 1), H * (u(n) * 3 - 1), alt), (10 ** (-1.2 + 0.9 * u(n, 1))).repeat(1, 3) *
+                   torch.tensor([1.0, 0.6, 0.1]), None, 0.004 + 0.02 * u(n, 1)))
+    means = torch.cat([x[0] for x in groups]); scales = torch.cat([x[1] for x in groups]).float()
+    P = means.shape[0]
+    rot = torch.randn(P, 4, generator=g); rot = rot / rot.norm(dim=1, keepdim=True)
+    opac = torch.cat([x[3] for x in groups]).float().clamp(1e-4, 0.99)
+    perm = torch.randperm(P, generator=g)                                         # mix the groups in depth
+    sc = S.Scene(means[perm].contiguous(), scales[perm].contiguous(), rot[perm].contiguous(), opac[perm].contiguous(),
+                 torch.rand(P, 3, generator=g))
+    dcol, dinv = S.upstream_grads(5, H, W, seed, True)
+    return dict(P=P, W=W, H=H, aa=False, mod=1.0, means3D=sc.means3D, scales=sc.scales, rotations=sc.rotations,
+                opacities=sc.opacities, colors=S.colors_precomp(sc, view), view=view, bg=S.background(seed),
+                dL_dcolor=dcol, dL_dinvdepth=dinv)
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libeogs_ref.so did not travel")
+@pytest.mark.parametrize("W,H,seed,aa", [(256, 192, 21, False), (250, 131, 22, False), (512, 512, 23, True), (96, 64, 24, False)])
+def test_adversarial_culling_against_compiled_reference(cuda_dev, W, H, seed, aa):
+    """patch_mask may only remove (pixel, Gaussian) pairs the per-pixel test would reject: on scenes built to sit on its
+    decision boundaries every image bit, n_contrib and final_T must still equal the reference's, and the gradients of
+    every Gaussian stay within the per-element bar (relative to the reference's own run-to-run noise)."""
+    c = adversarial_case(W, H, seed)
+    c["aa"] = aa
+    st, ex, g = run_mine(cuda_dev, c)
+    d = {k: (v.to(cuda_dev) if torch.is_tensor(v) else v) for k, v in c.items()}
+    empty, campos = torch.empty(0, device=cuda_dev), torch.zeros(3, device=cuda_dev)
+    rs = R.forward(d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], 1.0, empty,
+                   d["view"], d["view"], 1.0, 1.0, H, W, campos, False, aa)
+    rx = R.export_state(rs)
+    bw = lambda: R.backward(rs, d["bg"], d["means3D"], d["colors"], d["opacities"], d["scales"], d["rotations"], 1.0, empty,
+                            d["view"], d["view"], 1.0, 1.0, d["dL_dcolor"], d["dL_dinvdepth"], campos, aa)
+    gr, gr2 = bw(), bw()
+    torch.cuda.synchronize()
+    assert st.num_rendered == rs.num_rendered and st.num_rendered > c["P"]
+    for k in ("radii", "point_list", "ranges", "n_contrib"):
+        assert torch.equal(ex[k].long(), rx[k].long()), k
+    assert torch.equal(st.color.view(torch.int32), rs.color.view(torch.int32))
+    assert torch.equal(st.invdepth.view(torch.int32), rs.invdepth.view(torch.int32))
+    assert torch.equal(ex["final_T"].view(torch.int32), rx["final_T"].view(torch.int32))
+    names = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", None, "dL_dscales", "dL_drotations"]
+    for nm, t in zip(names, g):
+        if nm is None:
+            continue
+        assert torch.isfinite(t).all(), nm
+        if nm in ("dL_dmeans2D", "dL_dcolors", "dL_dopacity"):          # blend-level sums: directly comparable
+            assert_no_worse_than_rerun(t, gr[nm], gr2[nm], nm, GRAD_RTOL)
+        assert rel(t.cpu().numpy(), gr[nm].cpu().numpy()) < 5 * GRAD_RTOL, nm    # needles: the covariance chain is ill-conditioned
