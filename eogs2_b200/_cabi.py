@@ -24,6 +24,7 @@ SIGNATURES = {
     "eogs_image_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "eogs_binning_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_uint32]),
     "eogs_grad_scratch_floats": (C.c_size_t, [C.c_int]),
+    "eogs_point_list_words": (C.c_size_t, [C.c_uint32]),
     "eogs_forward_geometry": (C.c_int, [
         c_ptr, C.c_int, C.c_int, C.c_int, C.c_int,                 # stream, P, W, H, channels
         c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p,            # means3D, scales, rotations, cov3D, opacities, colors
@@ -106,7 +107,7 @@ SIGNATURES = {
         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 _lib = None
 
 

@@ -12,11 +12,11 @@
 // red.global.add.f32 run once per (tile, Gaussian) — 3.5x fewer on the bench scene — and there is
 // no block barrier and no cross-warp staging at all: everything is warp-synchronous.
 //
-//   staging   lane l fetches list entry (first - l) (3 x LDG.128, prefetched one batch ahead),
-//             computes its exact 8-bit patch mask (blend_common.cuh: which 8x4 patches can see
-//             alpha >= 1/255; patches whose pixels all stopped earlier are masked too), and
-//             stores the record to the warp's shared-memory stage; a ballot of non-empty masks
-//             is then walked bit by bit (back to front).
+//   staging   lane l owns list entry (first - l): it reads the entry's culling mask — one byte per instance,
+//             written by the forward blend (which 8x8 regions of the tile the Gaussian can reach with
+//             alpha >= 1/255; regions whose pixels all stopped earlier are masked too) — and only if the
+//             mask is non-empty gathers the record into the warp's shared-memory stage (cp.async, one batch
+//             ahead); a ballot of non-empty masks is then walked bit by bit (back to front).
 //   replay    per surviving entry and per set patch bit: recompute G and alpha with the
 //             forward's exact expression, vote, and for accepted pixels update T, the running
 //             "colour behind" dot product and the 11 accumulators.  Per-pixel constants
@@ -112,7 +112,7 @@ struct BwdWarpSmem {
     float4 rec[2][32][REC_F4];        // two stages of 32 packed records (cp.async destinations, 48 B each)
     uint32_t rid[2][32];              // Gaussian id of each staged record
     float cut[2][32];                 // alpha_cut of each staged record: accept iff power >= cut
-    int pmax[NPATCH];                 // max(n_contrib) over each 8x4 patch (warp-uniform; read once per batch)
+    int rmax[4];                      // max(n_contrib) over each 8x8 region (warp-uniform; read once per batch)
 #if EOGS_BWD_SMEM_FLUSH
     float red[6 + EOGS_MAX_CHANNELS][RED_STRIDE];   // flush: [value][lane], rows padded to 36 floats (LDS.128 of 8 lanes hit 8 bank groups)
 #endif
@@ -133,7 +133,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                  int tiles_x, int tiles_y, int band_row0, int band_h,
                  const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
                  const float* __restrict__ dL_dpix, const float* __restrict__ dL_dinvdepth,
-                 float* __restrict__ grad_rec,
+                 float* __restrict__ grad_rec, const uint8_t* __restrict__ masks,
                  const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ sched, uint32_t* queue)
 {
     constexpr int NV = 6 + C;   // mean2D.xy, conic.xyw, opacity, colours
@@ -143,8 +143,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     BwdWarpSmem& sm = s_warp[warp];
-    const float img_x1 = (float)(W - 1), img_y1 = (float)(H - 1);
-
     float bgv[C];
 #pragma unroll
     for (int ch = 0; ch < C; ch++) bgv[ch] = __ldg(bg + ch);
@@ -199,6 +197,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         f2 T2[NSTRIP], accum2[NSTRIP];
 #endif
         int nmax = 0;
+        int rmax_top[2] = {0, 0}, rmax_cur[2] = {0, 0};   // max(n_contrib) over the 8x8 regions of the current tile half
 #pragma unroll
         for (int r = 0; r < NSTRIP; r++) {
             float g[2][5], g_inv[2], Tf[2], nbg[2];
@@ -219,10 +218,11 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 }
                 g_inv[h] = (inside && dL_dinvdepth) ? __ldg(dL_dinvdepth + pix_id) : 0.f;
                 nbg[h] = -Tf[h] * bg_dot_g;
-                const int pm = __reduce_max_sync(FULL, ncon[p]);
-                if (lane == 0) sm.pmax[p] = pm;
+                const int pm = __reduce_max_sync(FULL, ncon[p]);     // warp-uniform
+                rmax_cur[h] = max(rmax_cur[h], pm);                  // region (R, c) = patches (2R, c) and (2R + 1, c)
                 nmax = max(nmax, pm);
             }
+            if (r == 1) { rmax_top[0] = rmax_cur[0]; rmax_top[1] = rmax_cur[1]; rmax_cur[0] = rmax_cur[1] = 0; }
             sm.pix[r][0][lane] = make_float4(g[0][0], g[1][0], g[0][1], g[1][1]);
             sm.pix[r][1][lane] = make_float4(g[0][2], g[1][2], g[0][3], g[1][3]);
             sm.pix[r][2][lane] = make_float4(g[0][4], g[1][4], g_inv[0], g_inv[1]);
@@ -241,56 +241,65 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #endif
         const int rounds = (nmax + 31) >> 5;
 
-        // Batch b, lane l holds list position nmax-1 - (32 b + l): back to front.  Records travel
-        // global -> shared with cp.async (no staging registers), one batch ahead of the replay.
-        uint32_t id_next = 0;
+        // Batch b, lane l holds list position nmax-1 - (32 b + l): back to front.  An entry's culling mask comes from
+        // the forward (one byte per instance, blend_fwd.cu: which 8x8 regions of the tile the Gaussian can reach);
+        // regions whose pixels all stopped earlier are masked too.  Only entries with a non-empty mask are fetched:
+        // their records travel global -> shared with cp.async (no staging registers), one batch ahead of the replay;
+        // ids and masks are prefetched two batches ahead.
+        const uint8_t* mlist = masks + range.x;
+        if (lane == 0) *reinterpret_cast<int4*>(&sm.rmax[0]) = make_int4(rmax_top[0], rmax_top[1], rmax_cur[0], rmax_cur[1]);
+        __syncwarp();
+        auto live_mask = [&](uint32_t raw, int pos) {
+            const int4 rm = *reinterpret_cast<const int4*>(&sm.rmax[0]);
+            const int rmv[4] = {rm.x, rm.y, rm.z, rm.w};
+            uint32_t m = pos >= 0 ? raw : 0u;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (pos >= rmv[q]) m &= ~(1u << q);                // every pixel of region q stopped before pos
+            return m;
+        };
+        auto fetch = [&](int stage, uint32_t id) {
+            sm.rid[stage][lane] = id;
+            const float4* src = splat + (size_t)id * REC_F4;
+#pragma unroll
+            for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[stage][lane][k], src + k);
+            cp_async4(&sm.cut[stage][lane], alpha_cut + id);
+        };
+        uint32_t id_next = 0u, m = 0u, m_next = 0u;
         {
             const int p0 = nmax - 1 - (int)lane;
-            if (p0 >= 0) {
-                const uint32_t id = __ldg(list + p0);
-                sm.rid[0][lane] = id;
-                const float4* src = splat + (size_t)id * REC_F4;
-#pragma unroll
-                for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[0][lane][k], src + k);
-                cp_async4(&sm.cut[0][lane], alpha_cut + id);
-            }
+            if (p0 >= 0) m = live_mask(__ldg(mlist + p0), p0);
+            if (m) fetch(0, __ldg(list + p0));
             cp_async_commit();
-            if (p0 - 32 >= 0) id_next = __ldg(list + p0 - 32);
+            if (p0 - 32 >= 0) {
+                m_next = live_mask(__ldg(mlist + p0 - 32), p0 - 32);
+                if (m_next) id_next = __ldg(list + p0 - 32);
+            }
         }
-
 
         int first = nmax - 1;                  // list position held by lane 0 in this batch
         for (int i = 0; i < rounds; i++, first -= 32) {
             const int pos = first - (int)lane;
             const int stage = i & 1;
             cp_async_wait<0>();                // this lane's record of batch i has landed
-            uint32_t m = 0u;
-            if (pos >= 0) m = patch_mask(sm.rec[stage][lane][0], sm.rec[stage][lane][1], tx0, ty0, img_x1, img_y1);
-            {
-                const int4 pm0 = *reinterpret_cast<const int4*>(&sm.pmax[0]), pm1 = *reinterpret_cast<const int4*>(&sm.pmax[4]);
-                const int pmv[NPATCH] = {pm0.x, pm0.y, pm0.z, pm0.w, pm1.x, pm1.y, pm1.z, pm1.w};
-#pragma unroll
-                for (int p = 0; p < NPATCH; p++)
-                    if (pos >= pmv[p]) m &= ~(1u << p);        // every pixel of patch p stopped before pos
-            }
             uint32_t todo = __ballot_sync(FULL, m != 0u);
             __syncwarp();                      // all lanes' records visible; previous batch's stage is free
 
             // next batch's records are in flight while this one is replayed
-            if (pos - 32 >= 0) {
-                sm.rid[stage ^ 1][lane] = id_next;
-                const float4* src = splat + (size_t)id_next * REC_F4;
-#pragma unroll
-                for (int k = 0; k < REC_F4; k++) cp_async16(&sm.rec[stage ^ 1][lane][k], src + k);
-                cp_async4(&sm.cut[stage ^ 1][lane], alpha_cut + id_next);
-            }
+            if (m_next) fetch(stage ^ 1, id_next);
             cp_async_commit();
-            if (pos - 64 >= 0) id_next = __ldg(list + pos - 64);
+            const uint32_t m_cur = m;
+            m = m_next;
+            m_next = 0u;
+            if (pos - 64 >= 0) {
+                m_next = live_mask(__ldg(mlist + pos - 64), pos - 64);
+                if (m_next) id_next = __ldg(list + pos - 64);
+            }
 
             while (todo) {
                 const int e = __ffs(todo) - 1;
                 todo &= todo - 1u;
-                const uint32_t me = __shfl_sync(FULL, m, e);
+                const uint32_t me = __shfl_sync(FULL, m_cur, e);
                 const int pos_e = first - e;
                 const float4 ra = sm.rec[stage][e][0];     // mean.x, mean.y, conic.x, conic.y
                 const float4 rb = sm.rec[stage][e][1];     // conic.z, opacity, c0, c1
@@ -349,7 +358,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #endif
                 };
 #if EOGS_BWD_HALF_SKIP
-                const bool top = (me & 0x0Fu) != 0u, bottom = (me & 0xF0u) != 0u;     // warp-uniform
+                const bool top = (me & 0x3u) != 0u, bottom = (me & 0xCu) != 0u;       // regions 0-1 = strips 0-1, regions 2-3 = strips 2-3 (warp-uniform)
                 if (top && bottom) {
 #pragma unroll
                     for (int r = 0; r < NSTRIP; r++) stage_a(r);
@@ -552,7 +561,7 @@ int launch_tile_order(cudaStream_t s, int W, int H, Band band, char* image, cons
 }
 
 int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
-                     const GeomLayout& GL, const uint32_t* point_list, const char* image,
+                     const GeomLayout& GL, const uint32_t* point_list, const uint8_t* masks, const char* image,
                      const ImageLayout& IL, const float* bg, const float* dL_dpix,
                      const float* dL_dinvdepth, float* grad_rec, uint32_t* queue)
 {
@@ -575,7 +584,7 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
             reinterpret_cast<const float4*>(geom + GL.splat), reinterpret_cast<const float*>(geom + GL.cut),
             bg, W, H, tiles_x, tiles_y,
             band.row_begin, band.height(H), reinterpret_cast<const float*>(image + IL.final_T),
-            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), dL_dpix, dL_dinvdepth, grad_rec,
+            reinterpret_cast<const uint32_t*>(image + IL.n_contrib), dL_dpix, dL_dinvdepth, grad_rec, masks,
             reinterpret_cast<const uint32_t*>(image + IL.tile_order),
             reinterpret_cast<const uint32_t*>(image + IL.sched), queue);
     };

@@ -1,12 +1,13 @@
-// Pieces shared by the forward and backward blend kernels: the exact patch-culling test, the warp
+// Pieces shared by the forward and backward blend kernels: the exact culling test, the warp
 // reduction of the backward's per-Gaussian terms, and the approximate MUFU wrappers.
 //
-// A 16x16 tile is cut into eight 8x4 pixel PATCHES (patch p: x in [8*(p&1), +7], y in [4*(p>>1), +3]).
-// The thread that stages a list entry decides ONCE which patches the Gaussian can reach with
-// alpha >= 1/255 (patch_mask below): the forward kernel (128 threads, warp = 8x8 region = two patches)
-// appends the entry only to the regions it reaches, the backward kernel (one warp per tile, lane = one
-// pixel of every patch) skips entries and half tiles nobody reaches.  The reference evaluates every
-// entry of the tile list in every one of the 256 threads (forward.cu:356-372, backward.cu:551-577).
+// A 16x16 tile is cut into four 8x8 pixel REGIONS (and, for the backward's pixel ownership, eight 8x4 patches:
+// patch p: x in [8*(p&1), +7], y in [4*(p>>1), +3]).  The forward thread that stages a list entry decides ONCE
+// which regions the Gaussian can reach with alpha >= 1/255 (region_mask below): the forward kernel (128 threads,
+// warp = one region) appends the entry only to the regions it reaches and stores the mask, one byte per instance;
+// the backward kernel (one warp per tile) reads it, never fetches entries nobody reaches and skips half tiles.
+// The reference evaluates every entry of the tile list in every one of the 256 threads (forward.cu:356-372,
+// backward.cu:551-577).
 // Culling is exact and conservative: it only removes (pixel, Gaussian) pairs that the per-pixel test
 // would reject, so images, n_contrib and gradients are unchanged; the tile lists stay the reference's.
 #pragma once
@@ -16,64 +17,17 @@ namespace eogs {
 
 constexpr int PATCH_W = 8, PATCH_H = 4;
 
-// 8-bit mask of the warp patches this Gaussian may contribute to (bit w = patch of warp w).
+// 4-bit mask of the 8x8 REGIONS of a tile (bit 2R + c: rows 8R..8R+7, columns 8c..8c+7) this Gaussian may contribute to.
 //
-// alpha >= 1/255 somewhere in a patch  <=>  the ellipse E = { p : q(p - m) <= qmax },
-// qmax = 2 ln(255 op), meets the patch rectangle.  E is cut by horizontal lines at the patch-row
+// alpha >= 1/255 somewhere in a region  <=>  the ellipse E = { p : q(p - m) <= qmax },
+// qmax = 2 ln(255 op), meets the region's rectangle.  E is cut by horizontal lines at the region-row
 // boundaries: on a line at offset dy from the centre, E spans x in [c - h, c + h] with
 // c = mx - (B/A) dy and h = sqrt(A qmax - det dy^2) / A.  Over a band between two lines the
 // right edge c + h is concave in dy, so its maximum is the bounding-box extreme mx + hx when the
 // extreme's dy = -(B/C) hx lies inside the band and otherwise sits on one of the two lines;
-// same for the left edge.  One sqrt per line (5 lines for 4 bands, bands widened by half a pixel
-// so neighbours share a line) gives all 8 answers exactly, for ~1/3 of the cost of eight independent
-// rectangle tests.  Margin 0.1 on q (0.05 on the exponent) covers rounding and the approximate
-// sqrt / divide; NaNs compare false and keep the entry.
-__device__ __forceinline__ uint32_t patch_mask(const float4& r0, const float4& r1, float tx0, float ty0,
-                                               float img_x1, float img_y1) {
-    constexpr int ROWS = TILE / PATCH_H, COLS = TILE / PATCH_W;
-    const float mx = r0.x, my = r0.y, A = r0.z, B = r0.w, C = r1.x, op = r1.y;
-    const float qmax = 2.f * __logf(255.f * op) + 0.1f;
-    if (qmax <= 0.f) return 0u;
-    const float det = A * C - B * B;
-    const float inv_det = __fdividef(1.f, det), invA = __fdividef(1.f, A);
-    const float hx = __fsqrt_rn(qmax * C * inv_det), hy = __fsqrt_rn(qmax * A * inv_det);
-    // whole-tile reject (also the common case): bounding box of E vs the tile
-    if (mx + hx < tx0 || mx - hx > tx0 + (TILE - 1) || my + hy < ty0 || my - hy > ty0 + (TILE - 1)) return 0u;
-    const float slope = -B * invA;
-    const float dy_right = __fdividef(-B * hx, C), dy_left = -dy_right;
-    const float Aq = A * qmax;
-
-    float dyl[ROWS + 1], xr[ROWS + 1], xl[ROWS + 1];
-#pragma unroll
-    for (int k = 0; k <= ROWS; k++) {
-        dyl[k] = (ty0 + (float)(PATCH_H * k) - 0.5f) - my;
-        const float dyc = fminf(fmaxf(dyl[k], -hy), hy);
-        const float h = __fsqrt_rn(fmaxf(0.f, Aq - det * dyc * dyc)) * invA;
-        const float c = mx + slope * dyc;
-        xr[k] = c + h;
-        xl[k] = c - h;
-    }
-    uint32_t m = 0u;
-#pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-        if (dyl[r + 1] < -hy || dyl[r] > hy) continue;                      // band misses E in y
-        if (ty0 + (float)(PATCH_H * r) > img_y1) continue;                  // band below the image
-        const float right = (dy_right > dyl[r] && dy_right < dyl[r + 1]) ? mx + hx : fmaxf(xr[r], xr[r + 1]);
-        const float left = (dy_left > dyl[r] && dy_left < dyl[r + 1]) ? mx - hx : fminf(xl[r], xl[r + 1]);
-#pragma unroll
-        for (int c = 0; c < COLS; c++) {
-            const float px0 = tx0 + (float)(PATCH_W * c);
-            if (px0 > img_x1) continue;
-            if (!(right < px0 - 0.01f || left > px0 + (PATCH_W - 1) + 0.01f)) m |= 1u << (r * COLS + c);
-        }
-    }
-    return m;
-}
-
-// 4-bit mask of the 8x8 REGIONS of a tile (bit 2R + c: rows 8R..8R+7, columns 8c..8c+7) the Gaussian may contribute
-// to — the forward kernel's granularity (one warp per region).  Same exact test as patch_mask with two row bands of 8
-// pixels instead of four of 4: three square roots instead of five, and by construction equal to OR-ing the two patch
-// bits of each region (an ellipse meets a union of boxes iff it meets one of them).
+// same for the left edge.  One sqrt per line (3 lines for 2 bands, bands widened by half a pixel
+// so neighbours share a line) gives all 4 answers exactly.  Margin 0.1 on q (0.05 on the exponent) covers rounding and
+// the approximate sqrt / divide; NaNs compare false and keep the entry.
 __device__ __forceinline__ uint32_t region_mask(const float4& r0, const float4& r1, float tx0, float ty0,
                                                 float img_x1, float img_y1) {
     constexpr int ROWS = 2, COLS = 2, RH = 8, RW = 8;

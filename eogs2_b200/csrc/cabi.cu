@@ -144,6 +144,7 @@ EOGS_API size_t eogs_image_bytes_band(int W, int H, int row_begin, int row_end) 
     return image_layout(W, H, b).total;
 }
 EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t I) { return binning_layout(W, H, I).total; }
+EOGS_API size_t eogs_point_list_words(uint32_t I) { return (size_t)I + ((size_t)I + 3) / 4; }
 EOGS_API size_t eogs_grad_scratch_floats(int P) { return (size_t)(P > 0 ? P : 0) * GRAD_STRIDE + GRAD_TAIL; }
 
 static int forward_geometry_impl(eogs_stream_t stream, int P, int W, int H, int channels,
@@ -253,7 +254,9 @@ EOGS_API int eogs_forward_render_band(eogs_stream_t stream, int P, int W, int H,
     const BinningLayout BL = binning_layout(W, H, num_instances);
     if (int rc = launch_binning(s, P, W, H, band, num_instances, static_cast<const char*>(geom), GL, point_list,
                                 static_cast<char*>(binning), BL, static_cast<char*>(image), IL)) return rc;
-    if (int rc = launch_blend_fwd(s, W, H, band, channels, static_cast<const char*>(geom), GL, point_list,
+    // one culling byte per instance lives behind the I ids of the point_list allocation (eogs_point_list_words)
+    uint8_t* masks = reinterpret_cast<uint8_t*>(point_list + num_instances);
+    if (int rc = launch_blend_fwd(s, W, H, band, channels, static_cast<const char*>(geom), GL, point_list, masks,
                                   static_cast<char*>(image), IL, bg, out_color, out_invdepth)) return rc;
     prof_mark(s, ST_BLEND_FWD);
     return 0;
@@ -304,7 +307,7 @@ EOGS_API int eogs_rasterize_forward(eogs_stream_t stream, int P, int W, int H, i
     void* binning = nullptr;
     *point_list = nullptr;
     if (info_host.num_instances > 0) {
-        *point_list = static_cast<uint32_t*>(alloc(user, 3, (size_t)info_host.num_instances * 4));
+        *point_list = static_cast<uint32_t*>(alloc(user, 3, eogs_point_list_words(info_host.num_instances) * 4));
         binning = alloc(user, 1, eogs_binning_bytes(W, H, info_host.num_instances));
         if (!*point_list || !binning) { set_error("allocation callback returned NULL"); return -5; }
     }
@@ -349,6 +352,7 @@ static int backward_impl(eogs_stream_t stream, int P, int W, int H, int channels
     if (num_instances > 0) {
         if (!point_list) { set_error("null point_list"); return -4; }
         if (int rc = launch_blend_bwd(s, W, H, band, channels, static_cast<const char*>(geom), GL, point_list,
+                                      reinterpret_cast<const uint8_t*>(point_list + num_instances),
                                       static_cast<const char*>(image), IL, bg, dL_dpix, dL_dinvdepth,
                                       grad_scratch, reinterpret_cast<uint32_t*>(grad_scratch + (size_t)P * GRAD_STRIDE))) return rc;
     }

@@ -137,11 +137,11 @@ int launch_binning(cudaStream_t s, int P, int W, int H, Band band, uint32_t I, c
                    const BinningLayout& BL, char* image, const ImageLayout& IL);
 
 int launch_blend_fwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
-                     const GeomLayout& GL, const uint32_t* point_list, char* image,
+                     const GeomLayout& GL, const uint32_t* point_list, uint8_t* masks, char* image,
                      const ImageLayout& IL, const float* bg, float* out_color, float* out_invdepth);
 
 int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, const char* geom,
-                     const GeomLayout& GL, const uint32_t* point_list, const char* image,
+                     const GeomLayout& GL, const uint32_t* point_list, const uint8_t* masks, const char* image,
                      const ImageLayout& IL, const float* bg, const float* dL_dpix,
                      const float* dL_dinvdepth, float* grad_rec, uint32_t* queue);
 

@@ -81,7 +81,7 @@ def forward_params_raw(bg, xyz, features_dc, opacity_logits, log_scales, raw_rot
         image = torch.empty(lib.eogs_image_bytes_band(W, H, rb, re), dtype=torch.uint8, device=dev)
         point_list = binning = None
         if num_rendered > 0:
-            point_list = torch.empty(num_rendered, dtype=torch.int32, device=dev)
+            point_list = torch.empty(lib.eogs_point_list_words(num_rendered), dtype=torch.int32, device=dev)
             binning = torch.empty(lib.eogs_binning_bytes(W, H, num_rendered), dtype=torch.uint8, device=dev)
         _cabi.check(lib.eogs_forward_render_band(
             stream, P, W, H, 5, rb, re, num_rendered, geom.data_ptr(), _ptr(point_list), _ptr(binning),

@@ -231,7 +231,7 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         point_list = None
         binning = None
         if num_rendered > 0:
-            point_list = torch.empty(num_rendered, dtype=torch.int32, device=dev)
+            point_list = torch.empty(lib.eogs_point_list_words(num_rendered), dtype=torch.int32, device=dev)
             binning = torch.empty(lib.eogs_binning_bytes(W, H, num_rendered), dtype=torch.uint8, device=dev)
         _cabi.check(lib.eogs_forward_render_band(
             stream, P, W, H, channels, rb, re, num_rendered, geom.data_ptr(), _ptr(point_list), _ptr(binning),
@@ -373,8 +373,8 @@ def export_state(state: ForwardState) -> dict:
                 out["means2D"].data_ptr(), out["depths"].data_ptr(), out["conic_opacity"].data_ptr(),
                 out["tiles_touched"].data_ptr(), _ptr(out["keys_sorted"]), out["ranges"].data_ptr(),
                 out["final_T"].data_ptr(), out["n_contrib"].data_ptr()), "eogs_export_state_band")
-        out["point_list"] = state.point_list if state.point_list is not None else \
-            torch.zeros((0,), dtype=torch.int32, device=dev)
+        out["point_list"] = state.point_list[:I] if state.point_list is not None else \
+            torch.zeros((0,), dtype=torch.int32, device=dev)        # (the I culling bytes behind the ids are internal)
         out["radii"] = state.radii
     return out
 

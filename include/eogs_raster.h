@@ -51,7 +51,7 @@ extern "C" {
 #define EOGS_API
 #endif
 
-#define EOGS_ABI_VERSION 6
+#define EOGS_ABI_VERSION 7
 #define EOGS_TILE 16            /* BLOCK_X = BLOCK_Y = 16, DGR/cuda_rasterizer/config.h:15-16 */
 #define EOGS_MAX_CHANNELS 5     /* NUM_CHANNELS 5,        DGR/cuda_rasterizer/config.h:14    */
 
@@ -94,6 +94,10 @@ EOGS_API size_t eogs_image_bytes(int W, int H);
  * Gaussian list, which is the separate `point_list` argument (4*I bytes) because it is
  * the only part backward needs. */
 EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t num_instances);
+/* 32-bit words of the `point_list` buffer for I instances: the I sorted Gaussian ids (identical to the reference's
+ * binningState.point_list, rasterizer_impl.h:56-61) followed by one culling byte per instance that the forward blend
+ * writes and the backward blend reads (which 8x8 regions of its tile the instance can reach). */
+EOGS_API size_t eogs_point_list_words(uint32_t num_instances);
 /* Floats of backward scratch for P Gaussians: one 16-float gradient record per Gaussian (what the
  * reference keeps in dL_dconic / dL_dmeans2D / dL_dopacity / dL_dcolors between its two backward
  * kernels, rasterize_points.cu:163-183) + a small tail holding the tile-queue counter of the blend
@@ -123,8 +127,8 @@ EOGS_API int eogs_forward_geometry(eogs_stream_t stream, int P, int W, int H, in
 /* Instance emission, tile sort, tile ranges, front-to-back alpha blend.  Replaces
  * duplicateWithKeys, cub SortPairs, identifyTileRanges (rasterizer_impl.cu:70-138,292-321)
  * and renderCUDA (forward.cu:288-411).
- *   point_list [I] u32 dev  out: Gaussian ids sorted by (tile, depth bits, id) — identical
- *                           to the reference's binningState.point_list
+ *   point_list [eogs_point_list_words(I)] u32 dev  out: first I words = Gaussian ids sorted by (tile, depth bits, id)
+ *                           — identical to the reference's binningState.point_list; then I culling bytes
  *   binning          dev    eogs_binning_bytes(W,H,I) bytes of scratch
  *   image            dev    eogs_image_bytes(W,H) bytes (kept for backward)
  *   bg [channels]    dev

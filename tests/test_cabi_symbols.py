@@ -20,7 +20,7 @@ def test_header_declares_the_boundary():
     names = declared_symbols()
     for must in ("eogs_forward_geometry", "eogs_forward_render", "eogs_rasterize_forward", "eogs_backward",
                  "eogs_mark_visible", "eogs_export_state", "eogs_geom_bytes", "eogs_image_bytes",
-                 "eogs_binning_bytes", "eogs_grad_scratch_floats", "eogs_last_error", "eogs_abi_version"):
+                 "eogs_binning_bytes", "eogs_grad_scratch_floats", "eogs_point_list_words", "eogs_last_error", "eogs_abi_version"):
         assert must in names
 
 
@@ -44,8 +44,9 @@ def test_only_the_c_abi_is_exported():
 def test_size_queries_are_host_only_and_monotonic():
     from eogs2_b200 import _cabi
     lib = _cabi.load()
-    assert lib.eogs_abi_version() == _cabi.ABI_VERSION == 6
+    assert lib.eogs_abi_version() == _cabi.ABI_VERSION == 7
     assert lib.eogs_grad_scratch_floats(1000) == 16 * 1000 + 16
+    assert lib.eogs_point_list_words(1001) == 1001 + 251
     g1, g2 = lib.eogs_geom_bytes(1000), lib.eogs_geom_bytes(1_000_000)
     assert 0 < g1 < g2 and g2 >= 1_000_000 * (48 + 4 + 8 + 4 * 6)
     assert lib.eogs_image_bytes(2048, 2048) >= 2048 * 2048 * 8 + 16384 * 8
