@@ -102,6 +102,10 @@ constexpr int RED_STRIDE = 36;
 #endif
 // 1: stage B runs strip PAIRS as straight-line code when both strips are live (two independent dependency
 // chains for the scheduler to interleave); 0: one strip per uniform branch.
+// 1: the per-pixel n_contrib of the lane's 8 pixels live in shared memory (the free half of pix[r][3]) instead of 8 registers
+#ifndef EOGS_BWD_NCON_SMEM
+#define EOGS_BWD_NCON_SMEM 0
+#endif
 #ifndef EOGS_BWD_PAIR_ILP
 #define EOGS_BWD_PAIR_ILP 0
 #endif
@@ -143,10 +147,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     BwdWarpSmem& sm = s_warp[warp];
-    float bgv[C];
-#pragma unroll
-    for (int ch = 0; ch < C; ch++) bgv[ch] = __ldg(bg + ch);
-
 #if EOGS_BWD_SMEM_FLUSH
     const int red_k = (int)(lane % NV), red_h = (int)(lane / NV);   // lane (k, h) adds columns [16h, 16h+16) of row k
     const int my_slot = lane < (uint32_t)NV ? (int)lane : -1;
@@ -196,6 +196,9 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #if !EOGS_BWD_STATE_SMEM
         f2 T2[NSTRIP], accum2[NSTRIP];
 #endif
+        float bgv[C];                          // per tile, so that it does not hold registers during the replay
+#pragma unroll
+        for (int ch = 0; ch < C; ch++) bgv[ch] = __ldg(bg + ch);
         int nmax = 0;
         int rmax_top[2] = {0, 0}, rmax_cur[2] = {0, 0};   // max(n_contrib) over the 8x8 regions of the current tile half
 #pragma unroll
@@ -226,7 +229,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             sm.pix[r][0][lane] = make_float4(g[0][0], g[1][0], g[0][1], g[1][1]);
             sm.pix[r][1][lane] = make_float4(g[0][2], g[1][2], g[0][3], g[1][3]);
             sm.pix[r][2][lane] = make_float4(g[0][4], g[1][4], g_inv[0], g_inv[1]);
-            sm.pix[r][3][lane] = make_float4(nbg[0], nbg[1], 0.f, 0.f);
+            sm.pix[r][3][lane] = make_float4(nbg[0], nbg[1], __int_as_float(ncon[2 * r]), __int_as_float(ncon[2 * r + 1]));
 #if EOGS_BWD_STATE_SMEM
             sm.state[r][lane] = make_float4(Tf[0], Tf[1], 0.f, 0.f);
 #else
@@ -345,14 +348,20 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     const float G0 = ex2_approx(lo2(pl2)), G1 = ex2_approx(hi2(pl2));
 #endif
                     // entry at list position pos_e is blended by a pixel iff pos_e < n_contrib (backward.cu:556-558)
-                    const bool v0 = pos_e < ncon[2 * r] && !(lo2(power2) > 0.0f) && !(lo2(power2) < cut_e);
-                    const bool v1 = pos_e < ncon[2 * r + 1] && !(hi2(power2) > 0.0f) && !(hi2(power2) < cut_e);
+#if EOGS_BWD_NCON_SMEM
+                    const float2 ncf = *reinterpret_cast<const float2*>(&sm.pix[r][3][lane].z);
+                    const int nc0 = __float_as_int(ncf.x), nc1 = __float_as_int(ncf.y);
+#else
+                    const int nc0 = ncon[2 * r], nc1 = ncon[2 * r + 1];
+#endif
+                    const bool v0 = pos_e < nc0 && !(lo2(power2) > 0.0f) && !(lo2(power2) < cut_e);
+                    const bool v1 = pos_e < nc1 && !(hi2(power2) > 0.0f) && !(hi2(power2) < cut_e);
                     Gv2[r] = mk2(v0 ? G0 : 0.f, v1 ? G1 : 0.f);       // one select per pixel: alpha follows from G
                     const f2 og2 = mul2(bc2(rb.y), Gv2[r]);
                     a2[r] = mk2(fminf(0.99f, lo2(og2)), fminf(0.99f, hi2(og2)));
                     lane_live |= (v0 || v1) ? (1u << r) : 0u;
 #if EOGS_COUNT_PAIRS
-                    cnt_eval += __popc(__ballot_sync(FULL, pos_e < ncon[2 * r])) + __popc(__ballot_sync(FULL, pos_e < ncon[2 * r + 1]));
+                    cnt_eval += __popc(__ballot_sync(FULL, pos_e < nc0)) + __popc(__ballot_sync(FULL, pos_e < nc1));
                     cnt_blend += __popc(__ballot_sync(FULL, v0)) + __popc(__ballot_sync(FULL, v1));
                     cnt_slots += 64ull;
 #endif
