@@ -61,6 +61,20 @@ def test_blend_kernels_use_packed_fp32x2_and_async_staging(kernels):
         assert c["BAR"] == 0                                    # warp-synchronous: no block barrier at all
 
 
+def test_backward_replay_does_not_rematerialise_addresses():
+    """At the 128-register cap ptxas has, twice during development, chosen to recompute shared-memory addresses from
+    SR_TID / SR_CgaCtaId inside the per-entry replay (S2R in the hot loop: 1.18 -> 1.29 ms on config 2).
+    Every special-register read of blend_bwd_kernel<5> must sit in the prologue, before the first record fetch."""
+    from eogs2_b200 import _cabi
+    sass = subprocess.run([cuobjdump, "-sass", str(_cabi.LIB_PATH)], capture_output=True, text=True).stdout
+    body = sass.split("blend_bwd_kernelILi5E", 1)[1].split("Function :", 1)[0]
+    ops = re.findall(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", body)
+    assert "LDGSTS.E.BYPASS.128" in ops and "REDUX.OR" in ops
+    first_fetch = ops.index("LDGSTS.E.BYPASS.128")
+    late = [i for i, o in enumerate(ops) if o == "S2R" and i > first_fetch]
+    assert not late, f"S2R at instruction {late} of {len(ops)} (first record fetch at {first_fetch})"
+
+
 def test_no_local_memory_in_hot_kernels(kernels):
     for frag in ("blend_fwd_kernel", "blend_bwd_kernel", "knn_search_kernel", "preprocess_bwd_kernel"):
         for c in find(kernels, frag):
