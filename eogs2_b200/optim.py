@@ -157,7 +157,8 @@ class FlatGaussianAdam:
     def densify_and_prune(self, xyz_gradient_accum: torch.Tensor, denom: torch.Tensor, grad_threshold: float,
                           min_opacity: float, screen_size_threshold: float, max_screen_size, scene_extent: float,
                           percent_dense: float = 0.01, N: int = 2,
-                          generator: Optional[torch.Generator] = None) -> Dict[str, torch.Tensor]:
+                          generator: Optional[torch.Generator] = None,
+                          noise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """GaussianModel.densify_and_prune (scene/gaussian_model.py:672-704) on the flat buffers: clone the small
         Gaussians with a large view-space gradient, split the large ones into N samples of their own
         distribution (parents removed), then prune by opacity (and, when max_screen_size is given, by world size
@@ -168,7 +169,9 @@ class FlatGaussianAdam:
         max_radii2D to zeros of the new length like densification_postfix (:569-571).
 
         `generator`: CUDA generator for the split samples; seed it identically on every rank (e.g. from the
-        iteration number) and the replicas stay bit-identical without a broadcast."""
+        iteration number) and the replicas stay bit-identical without a broadcast.
+        `noise`: the (N * K_split, 3) standard-normal draws themselves, in the reference's row order (N blocks of the
+        selected rows), instead of the generator — how tests/test_densify_gpu.py replays the reference's own run."""
         for need in ("xyz", "opacity", "scaling", "rotation"):
             if need not in self.slices:
                 raise ValueError(f"densify_and_prune needs the '{need}' segment")
@@ -189,7 +192,12 @@ class FlatGaussianAdam:
             split_off, split_cnt = self._scan_flags(lib, stream, split_flag[:P])
             Kc, Ks = (int(v) for v in torch.cat([clone_cnt, split_cnt]).tolist())      # one sync for both counts
             Pn = P + Kc + N * Ks
-            noise = torch.randn((N * Ks, 3), device=dev, dtype=torch.float32, generator=generator)
+            if noise is None:
+                noise = torch.randn((N * Ks, 3), device=dev, dtype=torch.float32, generator=generator)
+            else:
+                if tuple(noise.shape) != (N * Ks, 3):
+                    raise ValueError(f"noise must have shape ({N * Ks}, 3) for {Ks} split Gaussians, got {tuple(noise.shape)}")
+                noise = noise.to(device=dev, dtype=torch.float32).contiguous()
 
             old = (self.flat, self.exp_avg, self.exp_avg_sq, dict(self.slices))
             self._alloc(Pn)                                   # zeros: new rows start with zero moments

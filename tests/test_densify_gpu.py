@@ -1,4 +1,6 @@
-"""GPU: FlatGaussianAdam.densify_and_prune (csrc/optim.cu densify_* kernels) against a torch restatement of
+"""GPU: FlatGaussianAdam.densify_and_prune (csrc/optim.cu densify_* kernels) against (1) the reference's own run
+(tests/golden/densify_ref.npz, generated from /root/reference by tests/golden/make_golden_densify.py) and (2), at
+larger sizes and on the CUDA random stream, a torch restatement of
 GaussianModel.densify_and_clone / densify_and_split / densify_and_prune + cat_tensors_to_optimizer /
 _prune_optimizer (scene/gaussian_model.py:451-539, 573-704) on plain tensors, with the same random stream."""
 import pytest
@@ -111,3 +113,46 @@ def test_densify_is_rank_reproducible(cuda_dev):
                                            generator=torch.Generator(dev).manual_seed(1234)))
     for n in outs[0]:
         assert torch.equal(outs[0][n], outs[1][n])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_densify_and_adam_match_the_reference_run(cuda_dev, tag):
+    """tests/golden/densify_ref.npz: the reference's own GaussianModel (training_setup, two Adam steps,
+    add_densification_stats, densify_and_prune; scene/gaussian_model.py:223-271,451-704,719-723) executed on the CPU
+    of the build container by tests/golden/make_golden_densify.py.  Same initial tensors, gradients, statistics and
+    split draws here: the fused Adam must land on the reference's parameters / moments, and the densification on its
+    rows — order, copies, children and carried moments."""
+    import numpy as np
+    from pathlib import Path
+    dev = cuda_dev
+    z = np.load(Path(__file__).parent / "golden" / "densify_ref.npz")
+    t = lambda k: torch.from_numpy(z[k]).to(dev)                                   # noqa: E731
+    names = list(SHAPES)
+    lrs = {"xyz": float(z["lr_position_lr_init"]), "f_dc": float(z["lr_feature_lr"]), "opacity": float(z["lr_opacity_lr"]),
+           "scaling": float(z["lr_scaling_lr"]), "rotation": float(z["lr_rotation_lr"])}
+    flat = O.FlatGaussianAdam({n: t(f"{tag}_init_{n}") for n in names}, lrs)
+    for it in range(2):
+        flat.step(flat.pack({n: t(f"{tag}_grad{it}_{n}") for n in names}))
+    for n in names:
+        a, b = flat.slices[n]
+        ref_p, ref_m, ref_v = t(f"{tag}_before_{n}"), t(f"{tag}_before_m_{n}"), t(f"{tag}_before_v_{n}")
+        assert torch.allclose(flat.params[n], ref_p, rtol=1e-6, atol=1e-7), n
+        assert torch.allclose(flat.exp_avg[a:b].view_as(ref_m), ref_m, rtol=1e-6, atol=1e-12), n
+        assert torch.allclose(flat.exp_avg_sq[a:b].view_as(ref_v), ref_v, rtol=1e-6, atol=1e-15), n
+        # continue from the reference's exact state so the row comparison below is not blurred by Adam rounding
+        flat.flat[a:b].copy_(ref_p.reshape(-1)); flat.exp_avg[a:b].copy_(ref_m.reshape(-1)); flat.exp_avg_sq[a:b].copy_(ref_v.reshape(-1))
+    mss = int(z[f"{tag}_max_screen_size"])
+    new = flat.densify_and_prune(t(f"{tag}_accum"), t(f"{tag}_denom"), float(z["arg_grad_threshold"]), float(z["arg_min_opacity"]),
+                                 float(z["arg_screen_size_threshold"]), None if mss < 0 else mss, float(z["arg_scene_extent"]),
+                                 float(z["percent_dense"]), N=2, noise=t(f"{tag}_split_noise"))
+    assert flat.last_densify["cloned"] > 0 and 2 * flat.last_densify["split"] == z[f"{tag}_split_noise"].shape[0]
+    for n in names:
+        ref_p, ref_m, ref_v = t(f"{tag}_after_{n}"), t(f"{tag}_after_m_{n}"), t(f"{tag}_after_v_{n}")
+        assert new[n].shape == ref_p.shape, (n, new[n].shape, ref_p.shape)
+        a, b = flat.slices[n]
+        if n in ("xyz", "scaling"):                                                # children: R(q) * (std * z) + mean, log(std / 1.6)
+            assert torch.allclose(new[n], ref_p, rtol=1e-6, atol=1e-6), n
+        else:
+            assert torch.equal(new[n], ref_p), n
+        assert torch.equal(flat.exp_avg[a:b].view_as(ref_m), ref_m), n
+        assert torch.equal(flat.exp_avg_sq[a:b].view_as(ref_v), ref_v), n
