@@ -1,5 +1,7 @@
 // Backward blend, tile-per-warp: ONE WARP replays one 16x16 tile back to front, each lane owning
-// 8 pixels (one in each of the tile's eight 8x4 patches).  Replaces renderCUDA<5> backward
+// 8 pixels: the pixel PAIR (x, y), (x, y+4) — x = lane&7, y = lane>>3 — of each of the tile's four
+// 8x8 REGIONS, the forward's own pixel-to-lane map (blend_fwd.cu), so the forward's per-region
+// culling masks select exactly the units this kernel evaluates.  Replaces renderCUDA<5> backward
 // (DGR/cuda_rasterizer/backward.cu:458-643).
 //
 // Why a warp per tile.  The reference issues 12 atomicAdd(float) per contributing (pixel,
@@ -17,7 +19,7 @@
 //             alpha >= 1/255; regions whose pixels all stopped earlier are masked too) — and only if the
 //             mask is non-empty gathers the record into the warp's shared-memory stage (cp.async, one batch
 //             ahead); a ballot of non-empty masks is then walked bit by bit (back to front).
-//   replay    per surviving entry and per set patch bit: recompute G and alpha with the
+//   replay    per surviving entry and per set region bit: recompute G and alpha with the
 //             forward's exact expression, vote, and for accepted pixels update T, the running
 //             "colour behind" dot product and the 11 accumulators.  Per-pixel constants
 //             (dL_dpixel, T_final * bg.dL_dpixel) live in shared memory, lane-contiguous
@@ -60,15 +62,9 @@ int read_counters_bwd(unsigned long long* out, bool reset) {
     return 0;
 }
 
-#ifndef EOGS_BWD_WARPS
-#define EOGS_BWD_WARPS 4                     // tiles (= warps) per CTA: 4 = a 2x2 block of tiles, 2 = 2x1, 1 = one tile
-#endif
-constexpr int BWD_WARPS = EOGS_BWD_WARPS;
-constexpr int BWD_WX = BWD_WARPS >= 2 ? 2 : 1, BWD_WY = BWD_WARPS >= 4 ? 2 : 1;
-static_assert(BWD_WX * BWD_WY == BWD_WARPS, "EOGS_BWD_WARPS must be 1, 2 or 4");
+constexpr int BWD_WARPS = 4;                 // warps per CTA; every warp is an independent worker (no block barrier)
 constexpr int BWD_THREADS = BWD_WARPS * 32;
-constexpr int NPATCH = (TILE / PATCH_W) * (TILE / PATCH_H);   // 8
-constexpr int NSTRIP = NPATCH / 2;           // 4 strips of 16x4 pixels = a left and a right patch
+constexpr int NREGION = 4;                   // 8x8 regions of a tile: bit q of a culling mask = region (8*(q&1), 8*(q>>1))
 constexpr int RED_STRIDE = 36;
 
 // Accuracy switches for A/B builds (tools/fuzz_check.py): accurate expf / IEEE division instead of
@@ -79,58 +75,34 @@ constexpr int RED_STRIDE = 36;
 #ifndef EOGS_BWD_EXACT_DIV
 #define EOGS_BWD_EXACT_DIV 0
 #endif
-// Tuning switches (A/B measured on B200): where the per-pixel dynamic state lives.
-#ifndef EOGS_BWD_STATE_SMEM
-#define EOGS_BWD_STATE_SMEM 0                // 1: T / accum in shared memory (-16 registers, +2 LDS/STS per strip)
-#endif
-// 1: persistent warps.  Every warp pulls the next tile from a global queue (one atomicAdd per tile) that the
-// forward ordered longest-first (tile_order_kernel below: descending max(n_contrib), tiles nobody blended left
-// out).  A warp replays ~7 tiles per launch at the bench size and a heavy tile costs several average ones, so
-// the static tile -> CTA map left 15 % of the warp slots idle (ncu sm__warps_active 13.6 of 16: a CTA kept its
-// registers until its slowest warp finished, and the last CTAs of the grid ran alone).  0: one warp per tile of
-// a 2x2 block, static grid.
-#ifndef EOGS_BWD_PERSIST
-#define EOGS_BWD_PERSIST 1
-#endif
-// 1: stage A only for the half tiles (strips 0-1 / 2-3) the entry's patch mask reaches.
-#ifndef EOGS_BWD_HALF_SKIP
-#define EOGS_BWD_HALF_SKIP 1
-#endif
-// 1: cross-lane reduction of the flush through shared memory (see "flush" above); 0: transposing shuffle butterfly.
-#ifndef EOGS_BWD_SMEM_FLUSH
-#define EOGS_BWD_SMEM_FLUSH 1
-#endif
-// 1: stage B runs strip PAIRS as straight-line code when both strips are live (two independent dependency
-// chains for the scheduler to interleave); 0: one strip per uniform branch.
-// 1: the per-pixel n_contrib of the lane's 8 pixels live in shared memory (the free half of pix[r][3]) instead of 8 registers
+// 1: the per-pixel n_contrib of the lane's 8 pixels are read from shared memory (the free half of pix[q][3]) instead
+// of living in 8 registers — the kernel sits at the 128-register cap, where every live value less counts (DESIGN.md
+// section 4 on what ptxas does at the cap).  Measured 1.124 (1) vs 1.129 ms (0) on config 2.
 #ifndef EOGS_BWD_NCON_SMEM
-#define EOGS_BWD_NCON_SMEM 0
-#endif
-#ifndef EOGS_BWD_PAIR_ILP
-#define EOGS_BWD_PAIR_ILP 0
+#define EOGS_BWD_NCON_SMEM 1
 #endif
 
-// Per-pixel constants of a lane's pixel PAIR in strip r (left patch 2r, right patch 2r+1), laid out
+// Scheduling.  The warps are persistent: every warp pulls the next tile from a global queue (one atomicAdd per
+// tile) that the forward ordered longest-first (tile_order_kernel below: descending max(n_contrib), tiles nobody
+// blended left out).  A warp replays ~7 tiles per launch at the bench size and a heavy tile costs several average
+// ones; a static tile -> CTA map left 15 % of the warp slots idle (ncu sm__warps_active 13.6 of 16).
+
+// Per-pixel constants of a lane's pixel PAIR in region q (rows y and y+4: halves .a and .b), laid out
 // as the f32x2 operands the replay consumes: an LDS.128 lands two ready-made register pairs.
 struct BwdWarpSmem {
     float4 rec[2][32][REC_F4];        // two stages of 32 packed records (cp.async destinations, 48 B each)
     uint32_t rid[2][32];              // Gaussian id of each staged record
     float cut[2][32];                 // alpha_cut of each staged record: accept iff power >= cut
     int rmax[4];                      // max(n_contrib) over each 8x8 region (warp-uniform; read once per batch)
-#if EOGS_BWD_SMEM_FLUSH
     float red[6 + EOGS_MAX_CHANNELS][RED_STRIDE];   // flush: [value][lane], rows padded to 36 floats (LDS.128 of 8 lanes hit 8 bank groups)
-#endif
-    float4 pix[NSTRIP][4][32];        // [0] = {g0.L, g0.R, g1.L, g1.R}   [1] = {g2.L, g2.R, g3.L, g3.R}
-                                      // [2] = {g4.L, g4.R, ginv.L, ginv.R}
-                                      // [3] = {-T_final (bg . g).L, same .R, n_contrib.L, n_contrib.R (int bits)}
-#if EOGS_BWD_STATE_SMEM
-    float4 state[NSTRIP][32];         // dynamic per-pixel-pair state {T.L, T.R, accum.L, accum.R}
-#endif
+    float4 pix[NREGION][4][32];       // [0] = {g0.a, g0.b, g1.a, g1.b}   [1] = {g2.a, g2.b, g3.a, g3.b}
+                                      // [2] = {g4.a, g4.b, ginv.a, ginv.b}
+                                      // [3] = {-T_final (bg . g).a, same .b, n_contrib.a, n_contrib.b (int bits)}
 };                                    // g = dL_dpixel
 
 // 4 CTAs (16 warps) per SM measured best: 3 (142 regs) and 5 (96 regs) are both 14 % slower.
 template <int C>
-__global__ void __launch_bounds__(BWD_THREADS, 16 / BWD_WARPS)
+__global__ void __launch_bounds__(BWD_THREADS, 4)
 blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                  const float4* __restrict__ splat, const float* __restrict__ alpha_cut,
                  const float* __restrict__ bg, int W, int H,
@@ -147,12 +119,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     BwdWarpSmem& sm = s_warp[warp];
-#if EOGS_BWD_SMEM_FLUSH
     const int red_k = (int)(lane % NV), red_h = (int)(lane / NV);   // lane (k, h) adds columns [16h, 16h+16) of row k
     const int my_slot = lane < (uint32_t)NV ? (int)lane : -1;
-#else
-    const int my_slot = fold_slot<NV>(lane);
-#endif
     // The accumulators are kept un-scaled and un-signed; the constant factors of each gradient slot
     // are applied once per flush: mean2D gets -d(pixel)/d(ndc), the conic terms -1/2 (and the opacity, below).
     const float slot_scale = my_slot == 0 ? -0.5f * (float)W : my_slot == 1 ? -0.5f * (float)H :
@@ -162,56 +130,45 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #if EOGS_COUNT_PAIRS
     unsigned long long cnt_eval = 0ull, cnt_blend = 0ull, cnt_slots = 0ull, cnt_entries = 0ull, cnt_flush = 0ull;   // warp-uniform
 #endif
-#if EOGS_BWD_PERSIST
     const uint32_t n_active = __ldg(sched);                      // tiles with max(n_contrib) > 0, longest first
     for (;;) {
-        uint32_t q = 0;
-        if (lane == 0) q = atomicAdd(queue, 1u);
-        q = __shfl_sync(FULL, q, 0);
-        if (q >= n_active) break;
-        const uint32_t tile = __ldg(tile_order + q);
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(queue, 1u);
+        qi = __shfl_sync(FULL, qi, 0);
+        if (qi >= n_active) break;
+        const uint32_t tile = __ldg(tile_order + qi);
         const int tile_x = (int)(tile % (uint32_t)tiles_x), brow = (int)(tile / (uint32_t)tiles_x);
         (void)tiles_y;
-#else
-    {
-        (void)tile_order; (void)sched; (void)queue;
-        // tiles_y = tile rows of the band; brow = row inside the band, tile_y = row in the image
-        const int tile_x = (int)blockIdx.x * BWD_WX + (int)(warp % BWD_WX), brow = (int)blockIdx.y * BWD_WY + (int)(warp / BWD_WX);
-        if (tile_x >= tiles_x || brow >= tiles_y) return;        // whole warp leaves; no block barriers below
-#endif
         const int tile_y = brow + band_row0;
         const float tx0 = (float)(tile_x * TILE), ty0 = (float)(tile_y * TILE);
         const uint2 range = __ldg(ranges + (size_t)brow * tiles_x + tile_x);
         const uint32_t* list = point_list + range.x;
 
-        // ---- per-pixel state: pixel (patch p, lane) = (tile_x*16 + 8*(p&1) + (lane&7), tile_y*16 + 4*(p>>1) + (lane>>3))
+        // ---- per-pixel state: pixel (region q, half h, lane) = (tile_x*16 + 8*(q&1) + (lane&7), tile_y*16 + 8*(q>>1) + 4h + (lane>>3))
         const float pxl = tx0 + (float)(lane & 7u);
-        const f2 neg_px = mk2(-pxl, -(pxl + (float)PATCH_W));   // dx = mean.x - px as an add
-        const float py_lane = ty0 + (float)(lane >> 3);          // + 4r = the strip's pixel row (exact)
-        // dy = mean.y - py as an add, for the strip pairs (0, 1) and (2, 3)
-        const f2 neg_py01 = mk2(-py_lane, -(py_lane + (float)PATCH_H));
-        const f2 neg_py23 = mk2(-(py_lane + (float)(2 * PATCH_H)), -(py_lane + (float)(3 * PATCH_H)));
+        const f2 neg_px = mk2(-pxl, -(pxl + 8.f));               // dx = mean.x - px as an add: region columns 0 / 1
+        const float py_lane = ty0 + (float)(lane >> 3);
+        // dy = mean.y - py as an add, for the pixel pair of the upper (q = 0, 1) and the lower (q = 2, 3) regions
+        const f2 neg_py_up = mk2(-py_lane, -(py_lane + (float)PATCH_H));
+        const f2 neg_py_lo = mk2(-(py_lane + 8.f), -(py_lane + 8.f + (float)PATCH_H));
 
-        int ncon[NPATCH];
-#if !EOGS_BWD_STATE_SMEM
-        f2 T2[NSTRIP], accum2[NSTRIP];
-#endif
+        int ncon[2 * NREGION];
+        f2 T2[NREGION], accum2[NREGION];
         float bgv[C];                          // per tile, so that it does not hold registers during the replay
 #pragma unroll
         for (int ch = 0; ch < C; ch++) bgv[ch] = __ldg(bg + ch);
         int nmax = 0;
-        int rmax_top[2] = {0, 0}, rmax_cur[2] = {0, 0};   // max(n_contrib) over the 8x8 regions of the current tile half
+        int rmax[NREGION];                     // max(n_contrib) over each 8x8 region
 #pragma unroll
-        for (int r = 0; r < NSTRIP; r++) {
+        for (int q = 0; q < NREGION; q++) {
             float g[2][5], g_inv[2], Tf[2], nbg[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const int p = 2 * r + h;
-                const int px = tile_x * TILE + PATCH_W * h + (int)(lane & 7u);
-                const int py = tile_y * TILE + PATCH_H * r + (int)(lane >> 3);
+                const int px = tile_x * TILE + 8 * (q & 1) + (int)(lane & 7u);
+                const int py = tile_y * TILE + 8 * (q >> 1) + PATCH_H * h + (int)(lane >> 3);
                 const bool inside = px < W && py < H;
                 const size_t pix_id = (size_t)(py - band_row0 * TILE) * W + px;     // band-compact buffers
-                ncon[p] = inside ? (int)__ldg(n_contrib + pix_id) : 0;
+                ncon[2 * q + h] = inside ? (int)__ldg(n_contrib + pix_id) : 0;
                 Tf[h] = inside ? __ldg(final_T + pix_id) : 0.f;
                 float bg_dot_g = 0.f;
 #pragma unroll
@@ -221,27 +178,17 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 }
                 g_inv[h] = (inside && dL_dinvdepth) ? __ldg(dL_dinvdepth + pix_id) : 0.f;
                 nbg[h] = -Tf[h] * bg_dot_g;
-                const int pm = __reduce_max_sync(FULL, ncon[p]);     // warp-uniform
-                rmax_cur[h] = max(rmax_cur[h], pm);                  // region (R, c) = patches (2R, c) and (2R + 1, c)
-                nmax = max(nmax, pm);
             }
-            if (r == 1) { rmax_top[0] = rmax_cur[0]; rmax_top[1] = rmax_cur[1]; rmax_cur[0] = rmax_cur[1] = 0; }
-            sm.pix[r][0][lane] = make_float4(g[0][0], g[1][0], g[0][1], g[1][1]);
-            sm.pix[r][1][lane] = make_float4(g[0][2], g[1][2], g[0][3], g[1][3]);
-            sm.pix[r][2][lane] = make_float4(g[0][4], g[1][4], g_inv[0], g_inv[1]);
-            sm.pix[r][3][lane] = make_float4(nbg[0], nbg[1], __int_as_float(ncon[2 * r]), __int_as_float(ncon[2 * r + 1]));
-#if EOGS_BWD_STATE_SMEM
-            sm.state[r][lane] = make_float4(Tf[0], Tf[1], 0.f, 0.f);
-#else
-            T2[r] = mk2(Tf[0], Tf[1]);
-            accum2[r] = bc2(0.f);
-#endif
+            rmax[q] = __reduce_max_sync(FULL, max(ncon[2 * q], ncon[2 * q + 1]));     // warp-uniform
+            nmax = max(nmax, rmax[q]);
+            sm.pix[q][0][lane] = make_float4(g[0][0], g[1][0], g[0][1], g[1][1]);
+            sm.pix[q][1][lane] = make_float4(g[0][2], g[1][2], g[0][3], g[1][3]);
+            sm.pix[q][2][lane] = make_float4(g[0][4], g[1][4], g_inv[0], g_inv[1]);
+            sm.pix[q][3][lane] = make_float4(nbg[0], nbg[1], __int_as_float(ncon[2 * q]), __int_as_float(ncon[2 * q + 1]));
+            T2[q] = mk2(Tf[0], Tf[1]);
+            accum2[q] = bc2(0.f);
         }
-#if EOGS_BWD_PERSIST
         if (nmax == 0) continue;               // (cannot happen for a queued tile; kept for safety)
-#else
-        if (nmax == 0) return;                 // entries [nmax, n) were blended by no pixel of this tile
-#endif
         const int rounds = (nmax + 31) >> 5;
 
         // Batch b, lane l holds list position nmax-1 - (32 b + l): back to front.  An entry's culling mask comes from
@@ -250,7 +197,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
         // their records travel global -> shared with cp.async (no staging registers), one batch ahead of the replay;
         // ids and masks are prefetched two batches ahead.
         const uint8_t* mlist = masks + range.x;
-        if (lane == 0) *reinterpret_cast<int4*>(&sm.rmax[0]) = make_int4(rmax_top[0], rmax_top[1], rmax_cur[0], rmax_cur[1]);
+        if (lane == 0) *reinterpret_cast<int4*>(&sm.rmax[0]) = make_int4(rmax[0], rmax[1], rmax[2], rmax[3]);
         __syncwarp();
         auto live_mask = [&](uint32_t raw, int pos) {
             const int4 rm = *reinterpret_cast<const int4*>(&sm.rmax[0]);
@@ -315,27 +262,27 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                 for (int k = 0; k < NV; k++) v2[k] = bc2(0.f);
 
                 // the forward's exponent in its op order (forward.cu:361-365 as compiled: blend_fwd.cu), on the
-                // lane's (left, right) pixel pair; every half of a packed operation rounds like the scalar one,
-                // so `power` has the forward's bits and the accept decision below is the forward's
-                const f2 dx2 = add2(bc2(ra.x), neg_px);
-                const f2 zdx2 = mul2(bc2(ra.z), dx2);
-                const f2 wdx2 = mul2(bc2(ra.w), dx2);
-                const f2 dy01 = add2(bc2(ra.y), neg_py01), dy23 = add2(bc2(ra.y), neg_py23);
-                const f2 cyy01 = mul2(mul2(bc2(rb.x), dy01), dy01), cyy23 = mul2(mul2(bc2(rb.x), dy23), dy23);
-                const float dyv[NSTRIP] = {lo2(dy01), hi2(dy01), lo2(dy23), hi2(dy23)};
-                const float cyyv[NSTRIP] = {lo2(cyy01), hi2(cyy01), lo2(cyy23), hi2(cyy23)};
+                // lane's pixel pair (rows y, y+4 of a region; the pair shares dx); every half of a packed operation
+                // rounds like the scalar one, so `power` has the forward's bits and the accept decision below is
+                // the forward's
+                const f2 dxc2 = add2(bc2(ra.x), neg_px);               // .lo: region column 0, .hi: column 1
+                const f2 zdxc2 = mul2(bc2(ra.z), dxc2), wdxc2 = mul2(bc2(ra.w), dxc2);
+                const float dxv[2] = {lo2(dxc2), hi2(dxc2)}, zdxv[2] = {lo2(zdxc2), hi2(zdxc2)}, wdxv[2] = {lo2(wdxc2), hi2(wdxc2)};
+                const f2 dyr2[2] = {add2(bc2(ra.y), neg_py_up), add2(bc2(ra.y), neg_py_lo)};     // region rows 0 / 1
+                const f2 cyyr2[2] = {mul2(mul2(bc2(rb.x), dyr2[0]), dyr2[0]), mul2(mul2(bc2(rb.x), dyr2[1]), dyr2[1])};
 
-                // Stage A, branch-free over the strips it covers: G, alpha and the accept test of the lane's
+                // Stage A, per region the entry's mask reaches: G, alpha and the accept test of the lane's
                 // pixels depend only on geometry, never on the replay state, so the chains
-                // (FFMA2 -> ex2 -> select -> min) of the strips are independent and overlap each other's
+                // (FFMA2 -> ex2 -> select -> min) of the regions are independent and overlap each other's
                 // latency.  A rejected pixel gets G = alpha = 0, which leaves T, accum and every accumulator
-                // unchanged in stage B.  A patch whose mask bit is clear cannot be accepted (the mask is
-                // conservative), so the mask only decides which HALF tiles are evaluated at all.
-                f2 a2[NSTRIP], Gv2[NSTRIP];
-                uint32_t lane_live = 0u;                              // bit r: a pixel of THIS lane in strip r accepts this entry
-                auto stage_a = [&](const int r) {
-                    const f2 quad2 = fma2(dx2, zdx2, bc2(cyyv[r]));
-                    const f2 power2 = fma2(quad2, bc2(-0.5f), mul2(wdx2, bc2(-dyv[r])));
+                // unchanged in stage B.  A region whose mask bit is clear cannot be accepted (the mask is
+                // conservative) and is not evaluated at all.
+                f2 a2[NREGION], Gv2[NREGION];
+                uint32_t lane_live = 0u;                              // bit q: a pixel of THIS lane in region q accepts this entry
+                auto stage_a = [&](const int q) {
+                    const int c = q & 1, rr = q >> 1;
+                    const f2 quad2 = fma2(bc2(dxv[c]), bc2(zdxv[c]), cyyr2[rr]);
+                    const f2 power2 = fma2(quad2, bc2(-0.5f), neg2(mul2(bc2(wdxv[c]), dyr2[rr])));
                     // exp through ex2.approx (relative error ~2^-22): the VALUES carry a 1e-3 bar.  The accept
                     // DECISION alpha >= 1/255 must be the forward's, or a pixel on that contour flips and a whole
                     // term appears / disappears (1e-3..1e-2 in small scenes, tools/fuzz_parity.py).  It is taken on
@@ -349,72 +296,61 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #endif
                     // entry at list position pos_e is blended by a pixel iff pos_e < n_contrib (backward.cu:556-558)
 #if EOGS_BWD_NCON_SMEM
-                    const float2 ncf = *reinterpret_cast<const float2*>(&sm.pix[r][3][lane].z);
+                    const float2 ncf = *reinterpret_cast<const float2*>(&sm.pix[q][3][lane].z);
                     const int nc0 = __float_as_int(ncf.x), nc1 = __float_as_int(ncf.y);
 #else
-                    const int nc0 = ncon[2 * r], nc1 = ncon[2 * r + 1];
+                    const int nc0 = ncon[2 * q], nc1 = ncon[2 * q + 1];
 #endif
                     const bool v0 = pos_e < nc0 && !(lo2(power2) > 0.0f) && !(lo2(power2) < cut_e);
                     const bool v1 = pos_e < nc1 && !(hi2(power2) > 0.0f) && !(hi2(power2) < cut_e);
-                    Gv2[r] = mk2(v0 ? G0 : 0.f, v1 ? G1 : 0.f);       // one select per pixel: alpha follows from G
-                    const f2 og2 = mul2(bc2(rb.y), Gv2[r]);
-                    a2[r] = mk2(fminf(0.99f, lo2(og2)), fminf(0.99f, hi2(og2)));
-                    lane_live |= (v0 || v1) ? (1u << r) : 0u;
+                    Gv2[q] = mk2(v0 ? G0 : 0.f, v1 ? G1 : 0.f);       // one select per pixel: alpha follows from G
+                    const f2 og2 = mul2(bc2(rb.y), Gv2[q]);
+                    a2[q] = mk2(fminf(0.99f, lo2(og2)), fminf(0.99f, hi2(og2)));
+                    lane_live |= (v0 || v1) ? (1u << q) : 0u;
 #if EOGS_COUNT_PAIRS
                     cnt_eval += __popc(__ballot_sync(FULL, pos_e < nc0)) + __popc(__ballot_sync(FULL, pos_e < nc1));
                     cnt_blend += __popc(__ballot_sync(FULL, v0)) + __popc(__ballot_sync(FULL, v1));
                     cnt_slots += 64ull;
 #endif
                 };
-#if EOGS_BWD_HALF_SKIP
-                const bool top = (me & 0x3u) != 0u, bottom = (me & 0xCu) != 0u;       // regions 0-1 = strips 0-1, regions 2-3 = strips 2-3 (warp-uniform)
-                if (top && bottom) {
+                if (me == 0xFu) {                                     // straight-line: four independent chains
 #pragma unroll
-                    for (int r = 0; r < NSTRIP; r++) stage_a(r);
-                } else if (top) {
-                    stage_a(0); stage_a(1);
+                    for (int q = 0; q < NREGION; q++) stage_a(q);
                 } else {
-                    stage_a(2); stage_a(3);
-                }
-#else
-                (void)me;
 #pragma unroll
-                for (int r = 0; r < NSTRIP; r++) stage_a(r);
-#endif
+                    for (int q = 0; q < NREGION; q++)
+                        if ((me >> q) & 1u) stage_a(q);               // warp-uniform
+                }
                 const uint32_t live = __reduce_or_sync(FULL, lane_live);    // bit r: some pixel of strip r accepts (one REDUX)
                 const bool any = live != 0u;
 #if EOGS_COUNT_PAIRS
                 cnt_entries += 1ull; cnt_flush += any ? 1ull : 0ull;
 #endif
 
-                // Stage B: the sequential part (T, accum recurrences).  One 16x4 strip per step = one pixel
-                // PAIR per lane, all arithmetic packed (FFMA2).  Branch-free inside a strip.
+                // Stage B: the sequential part (T, accum recurrences).  One 8x8 region per step = one pixel
+                // PAIR per lane, all arithmetic packed (FFMA2).  Branch-free inside a region.
                 // Per-Gaussian sums kept per lane, with u = G dL/dalpha (so dL/dG = opacity u):
                 //   v2[0] = sum u dx   v2[1] = sum u dy   v2[2] = sum u dx dx   v2[3] = sum u dx dy   v2[4] = sum u dy dy
                 //   v2[5] = sum u      v2[6 + ch] = sum alpha T dL_dpixel[ch]
                 // The conic and the opacity are constants of the entry, so the mean gradient
                 // (backward.cu:631-632: dL_dG dG/ddelta) is assembled from the two first moments at flush time
-                // instead of per pixel: 27 packed operations per strip instead of 33.
-                auto stage_b = [&](const int r) {
-                    const float dy = dyv[r];
-                    const float4 pa = sm.pix[r][0][lane], pb = sm.pix[r][1][lane];
-                    const float4 pc = sm.pix[r][2][lane], pd = sm.pix[r][3][lane];
+                // instead of per pixel: 27 packed operations per region instead of 33.
+                auto stage_b = [&](const int q) {
+                    const float dx = dxv[q & 1];
+                    const f2 dy2 = dyr2[q >> 1];
+                    const float4 pa = sm.pix[q][0][lane], pb = sm.pix[q][1][lane];
+                    const float4 pc = sm.pix[q][2][lane], pd = sm.pix[q][3][lane];
                     const f2 g2[5] = {mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(pb.x, pb.y), mk2(pb.z, pb.w), mk2(pc.x, pc.y)};
                     const f2 ginv2 = mk2(pc.z, pc.w), nbg2 = mk2(pd.x, pd.y);
-#if EOGS_BWD_STATE_SMEM
-                    const float4 st = sm.state[r][lane];
-                    const f2 Told2 = mk2(st.x, st.y), accum_old2 = mk2(st.z, st.w);
-#else
-                    const f2 Told2 = T2[r], accum_old2 = accum2[r];
-#endif
-                    const f2 om2 = fma2(a2[r], bc2(-1.f), bc2(1.f));                // 1 - alpha
+                    const f2 Told2 = T2[q], accum_old2 = accum2[q];
+                    const f2 om2 = fma2(a2[q], bc2(-1.f), bc2(1.f));                // 1 - alpha
 #if EOGS_BWD_EXACT_DIV
                     const f2 inv2 = mk2(__fdiv_rn(1.f, lo2(om2)), __fdiv_rn(1.f, hi2(om2)));
 #else
                     const f2 inv2 = mk2(fast_rcp(lo2(om2)), fast_rcp(hi2(om2)));    // exactly 1 for a rejected pixel
 #endif
                     const f2 Tn2 = mul2(Told2, inv2);
-                    const f2 w2 = mul2(a2[r], Tn2);
+                    const f2 w2 = mul2(a2[q], Tn2);
                     f2 cg2 = mul2(bc2(rc.w), ginv2);
 #pragma unroll
                     for (int ch = 0; ch < C; ch++) {
@@ -424,40 +360,22 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     // accum = (colour blended behind this entry) . dL_dpixel
                     const f2 behind2 = fma2(accum_old2, bc2(-1.f), cg2);
                     const f2 dLa2 = fma2(nbg2, inv2, mul2(behind2, Tn2));           // dL/dalpha (finite; G = 0 below if rejected)
-                    const f2 acc_new2 = fma2(a2[r], behind2, accum_old2);
-#if EOGS_BWD_STATE_SMEM
-                    sm.state[r][lane] = make_float4(lo2(Tn2), hi2(Tn2), lo2(acc_new2), hi2(acc_new2));
-#else
-                    T2[r] = Tn2; accum2[r] = acc_new2;
-#endif
-                    const f2 u2 = mul2(Gv2[r], dLa2);
-                    const f2 ux2 = mul2(u2, dx2), uy2 = mul2(u2, bc2(dy));
+                    const f2 acc_new2 = fma2(a2[q], behind2, accum_old2);
+                    T2[q] = Tn2; accum2[q] = acc_new2;
+                    const f2 u2 = mul2(Gv2[q], dLa2);
+                    const f2 ux2 = mul2(u2, bc2(dx)), uy2 = mul2(u2, dy2);
                     v2[0] = add2(v2[0], ux2);
                     v2[1] = add2(v2[1], uy2);
-                    fma2_acc(v2[2], ux2, dx2);
-                    fma2_acc(v2[3], ux2, bc2(dy));
-                    fma2_acc(v2[4], uy2, bc2(dy));
+                    fma2_acc(v2[2], ux2, bc2(dx));
+                    fma2_acc(v2[3], ux2, dy2);
+                    fma2_acc(v2[4], uy2, dy2);
                     v2[5] = add2(v2[5], u2);
                 };
-#if EOGS_BWD_PAIR_ILP
-                if (live == 0xFu) {
-                    stage_b(0); stage_b(1); stage_b(2); stage_b(3);
-                } else {
 #pragma unroll
-                    for (int r = 0; r < NSTRIP; r += 2) {
-                        const uint32_t lv = (live >> r) & 3u;            // warp-uniform
-                        if (lv == 3u) { stage_b(r); stage_b(r + 1); }
-                        else if (lv == 1u) stage_b(r);
-                        else if (lv == 2u) stage_b(r + 1);
-                    }
+                for (int q = 0; q < NREGION; q++) {
+                    if (!((live >> q) & 1u)) continue;               // warp-uniform
+                    stage_b(q);
                 }
-#else
-#pragma unroll
-                for (int r = 0; r < NSTRIP; r++) {
-                    if (!((live >> r) & 1u)) continue;               // warp-uniform
-                    stage_b(r);
-                }
-#endif
                 if (any) {
                     const uint32_t gid = sm.rid[stage][e];
                     float v[NV];
@@ -470,7 +388,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     v[0] = fmaf(ocx, sx, ocy * sy);
                     v[1] = fmaf(ocz, sy, ocy * sx);
                     const float scale_e = slot_takes_op ? slot_scale * rb.y : slot_scale;
-#if EOGS_BWD_SMEM_FLUSH
                     __syncwarp();                                    // the previous flush's reads are done
 #pragma unroll
                     for (int k = 0; k < NV; k++) sm.red[k][lane] = v[k];
@@ -484,9 +401,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         v[0] = lo2(s) + hi2(s);
                     }
                     v[0] += __shfl_down_sync(FULL, v[0], NV);        // lane k < NV: its half + the half of lane k + NV
-#else
-                    warp_transpose_reduce<NV>(v, lane);
-#endif
                     if (my_slot >= 0) atomicAdd(grad_rec + (size_t)gid * GRAD_STRIDE + my_slot, v[0] * scale_e);
                 }
             }
@@ -575,14 +489,10 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
                      const float* dL_dinvdepth, float* grad_rec, uint32_t* queue)
 {
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = band.rows();
-#if EOGS_BWD_PERSIST
     // persistent: as many CTAs as fit on the device at once (4 per SM), never more warps than tiles
-    const int ctas_fit = sm_count_cached() * (16 / BWD_WARPS);
+    const int ctas_fit = sm_count_cached() * 4;
     const int ctas_need = (tiles_x * tiles_y + BWD_WARPS - 1) / BWD_WARPS;
     const dim3 grid(ctas_need < ctas_fit ? ctas_need : ctas_fit, 1, 1);
-#else
-    const dim3 grid((tiles_x + BWD_WX - 1) / BWD_WX, (tiles_y + BWD_WY - 1) / BWD_WY, 1);
-#endif
     constexpr size_t smem = sizeof(BwdWarpSmem) * BWD_WARPS;
     cudaError_t attr_err = cudaSuccess;
     auto run = [&](auto kernel) {
