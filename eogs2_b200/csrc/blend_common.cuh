@@ -68,49 +68,6 @@ __device__ __forceinline__ uint32_t region_mask(const float4& r0, const float4& 
     return m;
 }
 
-// ---- warp reduction of the backward's per-pair terms ------------------------------------------
-// Transposing butterfly level: N live values -> ceil(N/2), partner = lane ^ (1 << BIT).
-template <int N, int BIT>
-__device__ __forceinline__ void fold(float* v, uint32_t lane) {
-    constexpr int HALF = (N + 1) / 2;
-    const bool upper = (lane >> BIT) & 1u;
-#pragma unroll
-    for (int k = 0; k < HALF; k++) {
-        const float hi = (k + HALF < N) ? v[k + HALF] : 0.f;
-        const float keep = upper ? hi : v[k];
-        const float send = upper ? v[k] : hi;
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << BIT);
-    }
-}
-
-// After fold<N,4>, <N1,3>, <N2,2>, <N3,1> and a final xor-1 add, lane L holds the warp total of
-// value slot(L) in v[0]; returns -1 for lanes that hold nothing.
-template <int N>
-__device__ __forceinline__ int fold_slot(uint32_t lane) {
-    constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2, N4 = (N3 + 1) / 2;
-    static_assert(N4 == 1, "fold supports up to 16 values");
-    const int b1 = (lane >> 1) & 1, b2 = (lane >> 2) & 1, b3 = (lane >> 3) & 1, b4 = (lane >> 4) & 1;
-    int pos = b1 * N4;
-    if (pos >= N3) return -1;
-    pos += b2 * N3;
-    if (pos >= N2) return -1;
-    pos += b3 * N2;
-    if (pos >= N1) return -1;
-    pos += b4 * N1;
-    if (pos >= N) return -1;
-    return (lane & 1u) ? -1 : pos;
-}
-
-template <int N>
-__device__ __forceinline__ void warp_transpose_reduce(float* v, uint32_t lane) {
-    constexpr int N1 = (N + 1) / 2, N2 = (N1 + 1) / 2, N3 = (N2 + 1) / 2;
-    fold<N, 4>(v, lane);
-    fold<N1, 3>(v, lane);
-    fold<N2, 2>(v, lane);
-    fold<N3, 1>(v, lane);
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 __device__ __forceinline__ float fast_rcp(float x) {      // x in [0.01, 1]: no denormal handling needed
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
