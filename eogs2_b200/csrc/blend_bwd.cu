@@ -131,12 +131,21 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     unsigned long long cnt_eval = 0ull, cnt_blend = 0ull, cnt_slots = 0ull, cnt_entries = 0ull, cnt_flush = 0ull;   // warp-uniform
 #endif
     const uint32_t n_active = __ldg(sched);                      // tiles with max(n_contrib) > 0, longest first
+    // Small images: with fewer active tiles than resident warps the launch time is the replay of the LONGEST tile by
+    // one warp while most of the device idles (config 1, 512^2 = 1024 tiles: 87 us).  A tile is then split over 2 or 4
+    // warps by regions — a work item replays the tile's list for its region subset only (the other regions' n_contrib
+    // read as 0, which masks them everywhere below) and flushes its own partial sums.
+    const uint32_t slots = gridDim.x * BWD_WARPS;
+    const uint32_t split_log2 = 2u * n_active <= slots ? 2u : n_active <= slots ? 1u : 0u;
+    const uint32_t n_items = n_active << split_log2;
     for (;;) {
         uint32_t qi = 0;
         if (lane == 0) qi = atomicAdd(queue, 1u);
         qi = __shfl_sync(FULL, qi, 0);
-        if (qi >= n_active) break;
-        const uint32_t tile = __ldg(tile_order + qi);
+        if (qi >= n_items) break;
+        const uint32_t tile = __ldg(tile_order + (qi >> split_log2));
+        const uint32_t part = qi & ((1u << split_log2) - 1u);
+        const uint32_t region_set = split_log2 == 2u ? 1u << part : split_log2 == 1u ? 3u << (2u * part) : 0xFu;
         const int tile_x = (int)(tile % (uint32_t)tiles_x), brow = (int)(tile / (uint32_t)tiles_x);
         (void)tiles_y;
         const int tile_y = brow + band_row0;
@@ -166,7 +175,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
             for (int h = 0; h < 2; h++) {
                 const int px = tile_x * TILE + 8 * (q & 1) + (int)(lane & 7u);
                 const int py = tile_y * TILE + 8 * (q >> 1) + PATCH_H * h + (int)(lane >> 3);
-                const bool inside = px < W && py < H;
+                const bool inside = px < W && py < H && ((region_set >> q) & 1u);
                 const size_t pix_id = (size_t)(py - band_row0 * TILE) * W + px;     // band-compact buffers
                 ncon[2 * q + h] = inside ? (int)__ldg(n_contrib + pix_id) : 0;
                 Tf[h] = inside ? __ldg(final_T + pix_id) : 0.f;
@@ -489,9 +498,10 @@ int launch_blend_bwd(cudaStream_t s, int W, int H, Band band, int channels, cons
                      const float* dL_dinvdepth, float* grad_rec, uint32_t* queue)
 {
     const int tiles_x = (W + TILE - 1) / TILE, tiles_y = band.rows();
-    // persistent: as many CTAs as fit on the device at once (4 per SM), never more warps than tiles
+    // persistent: as many CTAs as fit on the device at once (4 per SM), never more warps than 4 per tile (the kernel
+    // splits tiles over warps when there are fewer active tiles than warps)
     const int ctas_fit = sm_count_cached() * 4;
-    const int ctas_need = (tiles_x * tiles_y + BWD_WARPS - 1) / BWD_WARPS;
+    const int ctas_need = tiles_x * tiles_y;
     const dim3 grid(ctas_need < ctas_fit ? ctas_need : ctas_fit, 1, 1);
     constexpr size_t smem = sizeof(BwdWarpSmem) * BWD_WARPS;
     cudaError_t attr_err = cudaSuccess;
