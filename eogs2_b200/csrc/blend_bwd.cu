@@ -305,8 +305,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #endif
                     // entry at list position pos_e is blended by a pixel iff pos_e < n_contrib (backward.cu:556-558)
 #if EOGS_BWD_NCON_SMEM
-                    const float2 ncf = *reinterpret_cast<const float2*>(&sm.pix[q][3][lane].z);
-                    const int nc0 = __float_as_int(ncf.x), nc1 = __float_as_int(ncf.y);
+                    const int2 ncp = *reinterpret_cast<const int2*>(&sm.pix[q][3][lane].z);
+                    const int nc0 = ncp.x, nc1 = ncp.y;
 #else
                     const int nc0 = ncon[2 * q], nc1 = ncon[2 * q + 1];
 #endif
@@ -348,7 +348,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     const float dx = dxv[q & 1];
                     const f2 dy2 = dyr2[q >> 1];
                     const float4 pa = sm.pix[q][0][lane], pb = sm.pix[q][1][lane];
-                    const float4 pc = sm.pix[q][2][lane], pd = sm.pix[q][3][lane];
+                    const float4 pc = sm.pix[q][2][lane];
+                    const float2 pd = *reinterpret_cast<const float2*>(&sm.pix[q][3][lane]);
                     const f2 g2[5] = {mk2(pa.x, pa.y), mk2(pa.z, pa.w), mk2(pb.x, pb.y), mk2(pb.z, pb.w), mk2(pc.x, pc.y)};
                     const f2 ginv2 = mk2(pc.z, pc.w), nbg2 = mk2(pd.x, pd.y);
                     const f2 Told2 = T2[q], accum_old2 = accum2[q];
