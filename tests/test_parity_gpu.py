@@ -285,7 +285,7 @@ def test_full_size_gradient_consistency(cuda_dev, full_case):
 
 
 # ------------------------------------------------------------------------------------------------
-# adversarial scenes aimed at the exact patch culling (csrc/blend_common.cuh: patch_mask) and at alpha_cut
+# adversarial scenes aimed at the exact region culling (csrc/blend_common.cuh: region_mask) and at alpha_cut
 def adversarial_case(W, H, seed, n_each=1500):
     """Gaussians built in PIXEL space (mapped back through the inverse camera) to sit where a conservative-but-wrong
     culling test would fail: needles with anisotropy up to 1e4 crossing patch corners, near-singular conics,
@@ -339,7 +339,7 @@ def adversarial_case(W, H, seed, n_each=1500):
 @pytest.mark.skipif(not R.available(), reason="oracle/_ref/libeogs_ref.so did not travel")
 @pytest.mark.parametrize("W,H,seed,aa", [(256, 192, 21, False), (250, 131, 22, False), (512, 512, 23, True), (96, 64, 24, False)])
 def test_adversarial_culling_against_compiled_reference(cuda_dev, W, H, seed, aa):
-    """patch_mask may only remove (pixel, Gaussian) pairs the per-pixel test would reject: on scenes built to sit on its
+    """region_mask may only remove (pixel, Gaussian) pairs the per-pixel test would reject: on scenes built to sit on its
     decision boundaries every image bit, n_contrib and final_T must still equal the reference's, and the gradients of
     every Gaussian stay within the per-element bar (relative to the reference's own run-to-run noise)."""
     c = adversarial_case(W, H, seed)

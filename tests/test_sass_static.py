@@ -56,14 +56,14 @@ def test_blend_kernels_use_packed_fp32x2_and_async_staging(kernels):
         assert c["LDGSTS"] >= 4
         # ONE red.global per (tile, Gaussian) flush; the only returning atomic is the tile-queue pull (one per tile)
         assert c["REDG"] == 1 and c["ATOMG"] == 1
-        assert c["REDUX"] >= 1                                  # per-entry strip liveness in one warp reduction
-        assert c["SHFL"] <= 16                                  # transposing butterfly: 13 shuffles for 11 values
+        assert c["REDUX"] >= 1                                  # per-entry region liveness in one warp reduction
+        assert c["SHFL"] <= 16                                  # one shuffle per entry / flush; no shuffle butterfly
         assert c["BAR"] == 0                                    # warp-synchronous: no block barrier at all
 
 
 def test_backward_replay_does_not_rematerialise_addresses():
     """At the 128-register cap ptxas has, twice during development, chosen to recompute shared-memory addresses from
-    SR_TID / SR_CgaCtaId inside the per-entry replay (S2R in the hot loop: 1.18 -> 1.29 ms on config 2).
+    SR_TID / SR_CgaCtaId inside the per-entry replay (S2R in the hot loop: 1.18 -> 1.29 ms on the bench scene).
     Every special-register read of blend_bwd_kernel<5> must sit in the prologue, before the first record fetch."""
     from eogs2_b200 import _cabi
     sass = subprocess.run([cuobjdump, "-sass", str(_cabi.LIB_PATH)], capture_output=True, text=True).stdout
