@@ -102,6 +102,8 @@ SIGNATURES = {
     "eogs_profile_read": (C.c_int, [c_ptr, C.c_int]),
     "eogs_debug_counters": (C.c_int, [c_ptr, C.c_int]),
     "eogs_debug_alpha_cut": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_ptr]),
+    "eogs_debug_depth_order_bytes": (C.c_size_t, [C.c_int]),
+    "eogs_debug_depth_order": (C.c_int, [c_ptr, C.c_int, c_ptr, c_ptr, c_ptr]),
     "eogs_export_state": (C.c_int, [
         c_ptr, C.c_int, C.c_int, C.c_int, C.c_uint32, c_ptr, c_ptr, c_ptr,
         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

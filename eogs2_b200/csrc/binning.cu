@@ -117,31 +117,57 @@ BinningLayout binning_layout(int W, int H, uint32_t I) {
 }
 
 // ---- stage 1b: depth order -------------------------------------------------------
-int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
-                       eogs_forward_info* info_dev)
+static int depth_order_impl(cudaStream_t s, int P, uint32_t* key_in, uint32_t* key_out, uint32_t* order, uint32_t* id_in,
+                            void* temp, size_t temp_bytes)
 {
-    uint32_t* key_in = reinterpret_cast<uint32_t*>(geom + L.key_in);
-    uint32_t* key_out = reinterpret_cast<uint32_t*>(geom + L.key_out);
-    uint32_t* id_in = reinterpret_cast<uint32_t*>(geom + L.id_in);
-    uint32_t* order = reinterpret_cast<uint32_t*>(geom + L.order);
-    void* temp = geom + L.temp;
-
     // (depth bits, id): keys are non-negative floats, so their bit patterns order like the
     // values; the radix sort is stable and ids come in ascending, which yields the tie order.
     size_t need = 0;
     cub::DoubleBuffer<uint32_t> keys(key_in, key_out);
-    // preprocess wrote 0..P-1 into `order` (see launch_preprocess_fwd): 4 passes land back in `order`
+    // `order` holds 0..P-1 (written by the preprocess kernel): 4 passes land back in `order`
     cub::DoubleBuffer<uint32_t> vals(order, id_in);
     EOGS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, vals, P, 0, 32, s));
-    if (need > L.temp_bytes) { set_error("depth sort temp %zu > %zu", need, L.temp_bytes); return -3; }
-    need = L.temp_bytes;
+    if (need > temp_bytes) { set_error("depth sort temp %zu > %zu", need, temp_bytes); return -3; }
+    need = temp_bytes;
     EOGS_CUDA(cub::DeviceRadixSort::SortPairs(temp, need, keys, vals, P, 0, 32, s));
     if (vals.Current() != order)
         EOGS_CUDA(cudaMemcpyAsync(order, vals.Current(), (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
-
-    (void)info_dev;      // num_instances was already published by the preprocess kernel
-    prof_mark(s, ST_DEPTH_SORT);
     return 0;
+}
+
+int launch_depth_order(cudaStream_t s, int P, char* geom, const GeomLayout& L,
+                       eogs_forward_info* info_dev)
+{
+    (void)info_dev;      // num_instances was already published by the preprocess kernel
+    const int rc = depth_order_impl(s, P, reinterpret_cast<uint32_t*>(geom + L.key_in), reinterpret_cast<uint32_t*>(geom + L.key_out),
+                                    reinterpret_cast<uint32_t*>(geom + L.order), reinterpret_cast<uint32_t*>(geom + L.id_in),
+                                    geom + L.temp, L.temp_bytes);
+    prof_mark(s, ST_DEPTH_SORT);
+    return rc;
+}
+
+__global__ void iota_kernel(int n, uint32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
+size_t debug_depth_order_bytes(int P) {
+    const size_t n = align_up((size_t)(P > 0 ? P : 1) * 4, 256);
+    return 3 * n + sort_temp_bound((size_t)(P > 0 ? P : 1));
+}
+
+int debug_depth_order(cudaStream_t s, int P, const uint32_t* keys, uint32_t* order, void* scratch)
+{
+    if (P <= 0) return 0;
+    const size_t n = align_up((size_t)P * 4, 256);
+    char* base = static_cast<char*>(scratch);
+    uint32_t* key_in = reinterpret_cast<uint32_t*>(base);
+    uint32_t* key_out = reinterpret_cast<uint32_t*>(base + n);
+    uint32_t* id_in = reinterpret_cast<uint32_t*>(base + 2 * n);
+    EOGS_CUDA(cudaMemcpyAsync(key_in, keys, (size_t)P * 4, cudaMemcpyDeviceToDevice, s));
+    iota_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, order);
+    EOGS_LAUNCH_CHECK("iota_kernel");
+    return depth_order_impl(s, P, key_in, key_out, order, id_in, base + 3 * n, sort_temp_bound((size_t)P));
 }
 
 // ---- stage 2: tile lists ------------------------------------------------------------------------

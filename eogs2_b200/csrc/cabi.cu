@@ -237,6 +237,14 @@ EOGS_API int eogs_debug_alpha_cut(eogs_stream_t stream, int n, const float* opac
     return launch_alpha_cut_debug(static_cast<cudaStream_t>(stream), n, opacity, cut, flags);
 }
 
+EOGS_API size_t eogs_debug_depth_order_bytes(int P) { return debug_depth_order_bytes(P); }
+EOGS_API int eogs_debug_depth_order(eogs_stream_t stream, int P, const uint32_t* keys, uint32_t* order, void* scratch)
+{
+    if (P < 0) { set_error("bad P"); return -1; }
+    if (P > 0 && (!keys || !order || !scratch)) { set_error("null argument"); return -4; }
+    return debug_depth_order(static_cast<cudaStream_t>(stream), P, keys, order, scratch);
+}
+
 EOGS_API int eogs_forward_render_band(eogs_stream_t stream, int P, int W, int H, int channels,
                         int row_begin, int row_end,
                         uint32_t num_instances, const void* geom, uint32_t* point_list,

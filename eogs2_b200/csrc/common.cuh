@@ -39,6 +39,9 @@ struct GeomLayout {
     size_t total;
 };
 
+size_t debug_depth_order_bytes(int P);
+int debug_depth_order(cudaStream_t s, int P, const uint32_t* keys, uint32_t* order, void* scratch);
+
 struct ImageLayout {
     size_t final_T;      // float[W*band_height]
     size_t n_contrib;    // u32[W*band_height]

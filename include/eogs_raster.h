@@ -385,6 +385,13 @@ EOGS_API int eogs_export_state(eogs_stream_t stream, int P, int W, int H, uint32
  * bit 1: it still accepts the next float below cut (must be 0). */
 EOGS_API int eogs_debug_alpha_cut(eogs_stream_t stream, int n, const float* opacity, float* cut, uint32_t* flags);
 
+/* The depth-order stage alone (test hook): order[P] = indices 0..P-1 sorted by (keys[i], i), keys = depth bit patterns
+ * with 0xFFFFFFFF for culled Gaussians, exactly what eogs_forward_geometry runs between projection and binning
+ * (the depth half of the reference's instance sort, rasterizer_impl.cu:306-311).
+ * scratch: device memory of eogs_debug_depth_order_bytes(P). */
+EOGS_API size_t eogs_debug_depth_order_bytes(int P);
+EOGS_API int eogs_debug_depth_order(eogs_stream_t stream, int P, const uint32_t* keys, uint32_t* order, void* scratch);
+
 /* Band variant: tiles_touched counts the band's tiles, keys_sorted carry whole-image tile ids,
  * ranges [band tiles,2], final_T / n_contrib [band_h*W]. */
 EOGS_API int eogs_export_state_band(eogs_stream_t stream, int P, int W, int H, int row_begin, int row_end,
