@@ -184,13 +184,11 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
         channels = int(colors.size(1))
 
     with torch.cuda.device(dev):
-        color = torch.zeros((channels, Hb, W), dtype=torch.float32, device=dev) if P == 0 else \
-            torch.empty((channels, Hb, W), dtype=torch.float32, device=dev)
-        invdepth = torch.zeros((1, Hb, W), dtype=torch.float32, device=dev) if P == 0 else \
-            torch.empty((1, Hb, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         if P == 0:
             # rasterize_points.cu:88 — nothing is launched; the image stays zero (not bg)
+            color = torch.zeros((channels, Hb, W), dtype=torch.float32, device=dev)
+            invdepth = torch.zeros((1, Hb, W), dtype=torch.float32, device=dev)
             return ForwardState(0, W, H, channels, 0, None, None, None, radii, color, invdepth, band)
 
         means3D = _f32c(means3D, "means3D", dev)
@@ -216,6 +214,10 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
             stream, P, W, H, channels, rb, re, _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp),
             _ptr(opacities), _ptr(colors), _ptr(viewmatrix), float(scale_modifier), int(bool(antialiasing)),
             radii.data_ptr(), geom.data_ptr(), info_dev, info_host.data_ptr()), "eogs_forward_geometry_band")
+        # everything the render stage needs is allocated while the projection kernel already runs
+        color = torch.empty((channels, Hb, W), dtype=torch.float32, device=dev)
+        invdepth = torch.empty((1, Hb, W), dtype=torch.float32, device=dev)
+        image = torch.empty(lib.eogs_image_bytes_band(W, H, rb, re), dtype=torch.uint8, device=dev)
         # The instance count sizes the binning buffers (reference: blocking cudaMemcpy,
         # rasterizer_impl.cu:284).
         num_rendered, err = _wait_info(info_np, dev)
@@ -227,7 +229,6 @@ def rasterize_forward_raw(bg, means3D, colors, opacities, scales, rotations, sca
             raise RuntimeError("Point is too high: a Gaussian's altitude exceeds 200 (depth = 200 - altitude < 0)")
         _debug_sync(debug, "preprocess")
 
-        image = torch.empty(lib.eogs_image_bytes_band(W, H, rb, re), dtype=torch.uint8, device=dev)
         point_list = None
         binning = None
         if num_rendered > 0:
