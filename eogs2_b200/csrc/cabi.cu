@@ -147,6 +147,27 @@ EOGS_API size_t eogs_binning_bytes(int W, int H, uint32_t I) { return binning_la
 EOGS_API size_t eogs_point_list_words(uint32_t I) { return (size_t)I + ((size_t)I + 3) / 4; }
 EOGS_API size_t eogs_grad_scratch_floats(int P) { return (size_t)(P > 0 ? P : 0) * GRAD_STRIDE + GRAD_TAIL; }
 
+// Device-side alias of a pinned host struct, or nullptr when the device cannot write it directly (cached per thread:
+// callers reuse one struct per stream).
+static eogs_forward_info* mapped_alias(eogs_forward_info* host)
+{
+    static thread_local eogs_forward_info* last_host = nullptr;
+    static thread_local eogs_forward_info* last_dev = nullptr;
+    static thread_local int last_device = -1;
+    if (!host) return nullptr;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (host == last_host && dev == last_device) return last_dev;
+    cudaPointerAttributes attr{};
+    eogs_forward_info* alias = nullptr;
+    if (cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        alias = static_cast<eogs_forward_info*>(attr.devicePointer);
+    else
+        (void)cudaGetLastError();
+    last_host = host; last_dev = alias; last_device = dev;
+    return alias;
+}
+
 static int forward_geometry_impl(eogs_stream_t stream, int P, int W, int H, int channels,
                           int row_begin, int row_end, bool raw_params, const float* alt_affine,
                           const float* means3D, const float* scales, const float* rotations,
@@ -164,25 +185,30 @@ static int forward_geometry_impl(eogs_stream_t stream, int P, int W, int H, int 
     if (!means3D || !opacities || !viewmatrix || !radii || !geom || !info_dev) { set_error("null argument"); return -4; }
     EOGS_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(eogs_forward_info), s));
     prof_begin(s);
+    // The host needs I once per forward.  Its copy to the host's pinned struct is enqueued right after the projection
+    // kernel, BEFORE the depth sort: a host that polls info_host->ready has I while the sort runs and can enqueue the
+    // render stage behind it — the GPU never waits for the host round trip (the reference blocks on a cudaMemcpy after
+    // its scan, rasterizer_impl.cu:284).  Small scenes: the kernel's last warp writes the pinned struct itself (when it
+    // is mapped into the device address space, which cudaHostAlloc / torch pin_memory memory is), see preprocess.cu.
+    constexpr int DIRECT_PUBLISH_MAX_P = 1 << 18;
+    eogs_forward_info* host_mapped = (P > 0 && P <= DIRECT_PUBLISH_MAX_P) ? mapped_alias(info_host) : nullptr;
     if (P > 0) {
         const GeomLayout L = geom_layout(P);
         char* g = static_cast<char*>(geom);
         if (int rc = launch_preprocess_fwd(s, P, W, H, band, channels, raw_params, means3D, scales, rotations,
                                            cov3D_precomp, opacities, colors, viewmatrix, alt_affine, scale_modifier,
-                                           antialiasing != 0, radii, g, L, info_dev)) return rc;
+                                           antialiasing != 0, radii, g, L, info_dev, host_mapped)) return rc;
         prof_mark(s, ST_PREPROCESS);
     }
-    // The preprocess kernel has published I and the error word: hand them to the host NOW, with the `ready` word
-    // set, and only then enqueue the depth sort and the scan.  A host that polls info_host->ready (pinned memory)
-    // gets I while those still run and can enqueue the render stage behind them: the GPU never waits for the host
-    // round trip (the reference blocks on a cudaMemcpy after its scan, rasterizer_impl.cu:284).
-    // Two stream-ordered copies: the payload (I, error) first, the `ready` word second.  A host that sees `ready` set
-    // therefore reads a complete payload (one 16-byte copy gives no such guarantee: CUDA does not promise that a host
-    // thread observes a device -> host copy atomically or in word order before the stream operation completes).
-    EOGS_CUDA(cudaMemsetAsync(&info_dev->ready, 0x01, sizeof(uint32_t), s));
-    if (info_host) {
-        EOGS_CUDA(cudaMemcpyAsync(info_host, info_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        EOGS_CUDA(cudaMemcpyAsync(&info_host->ready, &info_dev->ready, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (!host_mapped) {
+        // Two stream-ordered copies: the payload (I, error) first, the `ready` word second.  A host that sees `ready` set
+        // therefore reads a complete payload (one 16-byte copy gives no such guarantee: CUDA does not promise that a host
+        // thread observes a device -> host copy atomically or in word order before the stream operation completes).
+        EOGS_CUDA(cudaMemsetAsync(&info_dev->ready, 0x01, sizeof(uint32_t), s));
+        if (info_host) {
+            EOGS_CUDA(cudaMemcpyAsync(info_host, info_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            EOGS_CUDA(cudaMemcpyAsync(&info_host->ready, &info_dev->ready, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        }
     }
     if (P > 0) {
         if (int rc = launch_depth_order(s, P, static_cast<char*>(geom), geom_layout(P), info_dev)) return rc;

@@ -128,7 +128,8 @@ int launch_preprocess_fwd(cudaStream_t s, int P, int W, int H, Band band, int ch
                           const float* means3D, const float* scales, const float* rotations,
                           const float* cov3D_precomp, const float* opacities, const float* colors,
                           const float* view, const float* alt_affine, float scale_modifier, bool antialiasing,
-                          int32_t* radii, char* geom, const GeomLayout& L, eogs_forward_info* info_dev);
+                          int32_t* radii, char* geom, const GeomLayout& L, eogs_forward_info* info_dev,
+                          eogs_forward_info* info_host_mapped);
 
 int launch_alpha_cut_debug(cudaStream_t s, int n, const float* op, float* cut, uint32_t* flags);
 

@@ -62,15 +62,17 @@ extern "C" {
 
 typedef void* eogs_stream_t;    /* cudaStream_t */
 
-/* Host-visible result of the geometry stage (write target must be pinned host memory).  The copy to
- * info_host is enqueued right after the projection kernel, BEFORE the depth sort and the scan: a host that
- * zeroes info_host->ready before the call and polls it afterwards has I while the rest of the geometry stage
- * still runs; a host that synchronises the stream sees the same values. */
+/* Host-visible result of the geometry stage.  info_host must be pinned host memory.  Its words are written right after
+ * the projection kernel, BEFORE the depth sort — by two stream-ordered copies (payload, then `ready`), or, for scenes of
+ * up to 2^18 Gaussians whose info_host is mapped into the device address space (cudaHostAlloc / cudaMallocHost / torch
+ * pin_memory under unified addressing), by the kernel's last warp itself (payload, system-scope fence, `ready`): a host
+ * that zeroes info_host->ready before the call and polls it afterwards has I while the rest of the geometry stage still
+ * runs; a host that synchronises the stream sees the same values. */
 typedef struct eogs_forward_info {
     uint32_t num_instances;     /* I = sum of tiles touched = reference's num_rendered */
     uint32_t error;             /* EOGS_ERR_* bits */
     uint32_t ready;             /* non-zero once num_instances / error are final */
-    uint32_t reserved;
+    uint32_t reserved;          /* device copy: warps of the projection kernel that have published (internal) */
 } eogs_forward_info;
 
 EOGS_API int eogs_abi_version(void);
