@@ -211,8 +211,12 @@ def ours_e2e_factory(wl, dev, world=1):
             means3D=t["means3D"], means2D=means2D, opacities=t["opacities"], colors_precomp=t["colors"],
             scales=t["scales"], rotations=t["rotations"])
         pipe.submit(hsub)                   # next step's H2D (one copy per step) overlaps this step's blend kernels
-        loss = (color * wl["dcol"]).sum()
-        loss.backward()
+        # the upstream gradient dL/dcolor = dcol is handed to autograd directly (what `(color * dcol).sum().backward()`
+        # produces, without autograd's broadcast-multiply kernel — the reference arm calls its backward with dcol too);
+        # the loss itself is still computed for the read-back
+        with torch.no_grad():
+            loss = (color * wl["dcol"]).sum()
+        torch.autograd.backward(color, wl["dcol"])
         if bucket is not None:
             # the step is not finished before the gradients are summed over ranks
             bucket.params, bucket.extras = t, {"viewmatrix": view}
