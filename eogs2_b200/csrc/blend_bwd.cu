@@ -123,9 +123,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int my_slot = lane < (uint32_t)NV ? (int)lane : -1;
     // The accumulators are kept un-scaled and un-signed; the constant factors of each gradient slot
     // are applied once per flush: mean2D gets -d(pixel)/d(ndc), the conic terms -1/2 (and the opacity, below).
-    const float slot_scale = my_slot == 0 ? -0.5f * (float)W : my_slot == 1 ? -0.5f * (float)H :
-                             (my_slot >= 2 && my_slot <= 4) ? -0.5f : 1.f;
-    const bool slot_takes_op = my_slot >= 2 && my_slot <= 4;
+    const float slot_scale = (my_slot >= 2 && my_slot <= 4) ? -0.5f : 1.f;       // the conic sums carry their -1/2
 
 #if EOGS_COUNT_PAIRS
     unsigned long long cnt_eval = 0ull, cnt_blend = 0ull, cnt_slots = 0ull, cnt_entries = 0ull, cnt_flush = 0ull;   // warp-uniform
@@ -391,13 +389,10 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                     float v[NV];
 #pragma unroll
                     for (int k = 0; k < NV; k++) v[k] = lo2(v2[k]) + hi2(v2[k]);
-                    // dL_dmean2D (pixel units) = opacity * conic . (sum u dx, sum u dy); the conic sums and their -1/2
-                    // take the opacity with the slot scale
-                    const float ocx = __fmul_rn(rb.y, ra.z), ocy = __fmul_rn(rb.y, ra.w), ocz = __fmul_rn(rb.y, rb.x);
-                    const float sx = v[0], sy = v[1];
-                    v[0] = fmaf(ocx, sx, ocy * sy);
-                    v[1] = fmaf(ocz, sy, ocy * sx);
-                    const float scale_e = slot_takes_op ? slot_scale * rb.y : slot_scale;
+                    // The record receives the plain sums: everything that is constant per Gaussian — the opacity on the
+                    // five geometric sums, the conic that turns the two first moments into dL_dmean2D, the pixel -> ndc
+                    // factors — is applied once per Gaussian by preprocess_bwd_kernel (linear, so it commutes with the sum
+                    // over tiles) instead of once per (tile, Gaussian) here.
                     __syncwarp();                                    // the previous flush's reads are done
 #pragma unroll
                     for (int k = 0; k < NV; k++) sm.red[k][lane] = v[k];
@@ -411,7 +406,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         v[0] = lo2(s) + hi2(s);
                     }
                     v[0] += __shfl_down_sync(FULL, v[0], NV);        // lane k < NV: its half + the half of lane k + NV
-                    if (my_slot >= 0) atomicAdd(grad_rec + (size_t)gid * GRAD_STRIDE + my_slot, v[0] * scale_e);
+                    if (my_slot >= 0) atomicAdd(grad_rec + (size_t)gid * GRAD_STRIDE + my_slot, v[0] * slot_scale);
                 }
             }
             __syncwarp();

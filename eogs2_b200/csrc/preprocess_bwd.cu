@@ -32,7 +32,7 @@ constexpr int NSUMS = 14;
 //   dL_dscales    -> dL_dlog_scale  = dL_ds * s
 //   dL_drotations -> dL_draw_quat   = (dL_dq - q (q . dL_dq)) / max(|r|, 1e-12)
 template <int C, bool RAW>
-__global__ void __launch_bounds__(PBW_THREADS)
+__global__ void __launch_bounds__(PBW_THREADS, 3)
 preprocess_bwd_kernel(int P, int W, int H, const float* __restrict__ alt_affine, float* __restrict__ alt_sums,
                       const float* __restrict__ means3D, const float* __restrict__ scales,
                       const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
@@ -68,8 +68,13 @@ preprocess_bwd_kernel(int P, int W, int H, const float* __restrict__ alt_affine,
             const float4 ga = __ldg(grad_rec + (size_t)idx * (GRAD_STRIDE / 4));
             const float4 gb = __ldg(grad_rec + (size_t)idx * (GRAD_STRIDE / 4) + 1);
             const float4 gc = __ldg(grad_rec + (size_t)idx * (GRAD_STRIDE / 4) + 2);
-            g_mean2D[0] = ga.x; g_mean2D[1] = ga.y;
-            const float dcon_x = ga.z, dcon_y = ga.w, dcon_w = gb.x;
+            // The blend backward accumulated plain sums over the Gaussian's pixels (u = G dL/dalpha):
+            //   ga.x, ga.y = sum u dx, sum u dy;   ga.z, ga.w, gb.x = -1/2 sum u (dx dx, dx dy, dy dy);   gb.y = sum u
+            // The per-Gaussian constants are applied below, once the conic and the opacity are recomputed:
+            //   dL_dconic = opacity * (ga.z, ga.w, gb.x)                                     (backward.cu:634-640)
+            //   dL_dmean2D = -(W/2, H/2) * opacity * conic . (sum u dx, sum u dy)            (backward.cu:631-632)
+            const float mom_x = ga.x, mom_y = ga.y;
+            float dcon_x = ga.z, dcon_y = ga.w, dcon_w = gb.x;
             g_op = gb.y;
             g_col[0] = gb.z; g_col[1] = gb.w; g_col[2] = gc.x; g_col[3] = gc.y; g_col[4] = gc.z;
 
@@ -113,12 +118,14 @@ preprocess_bwd_kernel(int P, int W, int H, const float* __restrict__ alt_affine,
             // ---- computeCov2DCUDA (backward.cu:198-251) ----
             constexpr float h_var = 0.3f;
             float dL_dc_xx = 0.f, dL_dc_xy = 0.f, dL_dc_yy = 0.f;
+            float aa_scale = 1.f;                          // the forward's opacity factor (forward.cu:229-235)
             if (antialiasing) {
                 const float det_cov = c_xx * c_yy - c_xy * c_xy;
                 c_xx += h_var; c_yy += h_var;
                 const float det_plus = c_xx * c_yy - c_xy * c_xy;
                 const float ratio = det_cov / det_plus;
                 const float h_scale = sqrtf(fmaxf(0.000025f, ratio));
+                aa_scale = h_scale;
                 const float d_h = g_op * (RAW ? op_act : __ldg(opacities + idx));
                 g_op = g_op * h_scale;
                 const float d_inside_root = ratio <= 0.000025f ? 0.f : d_h / (2.f * h_scale);
@@ -132,6 +139,14 @@ preprocess_bwd_kernel(int P, int W, int H, const float* __restrict__ alt_affine,
                 c_xx += h_var; c_yy += h_var;
             }
             const float denom = c_xx * c_yy - c_xy * c_xy;
+            {
+                const float op_fwd = (RAW ? op_act : __ldg(opacities + idx)) * aa_scale;      // opacity as the forward stored it
+                const float det_inv = __fdiv_rn(1.f, denom);                 // conic = (c_yy, -c_xy, c_xx) / det (forward.cu:239-241)
+                const float con_x = c_yy * det_inv, con_y = -c_xy * det_inv, con_z = c_xx * det_inv;
+                g_mean2D[0] = -0.5f * (float)W * op_fwd * (con_x * mom_x + con_y * mom_y);
+                g_mean2D[1] = -0.5f * (float)H * op_fwd * (con_z * mom_y + con_y * mom_x);
+                dcon_x *= op_fwd; dcon_y *= op_fwd; dcon_w *= op_fwd;
+            }
             const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
             if (denom2inv != 0.f) {
                 dL_dc_xx += denom2inv * (-c_yy * c_yy * dcon_x + 2.f * c_xy * c_yy * dcon_y + (denom - c_xx * c_yy) * dcon_w);
