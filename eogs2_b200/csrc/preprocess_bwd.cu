@@ -32,7 +32,7 @@ constexpr int NSUMS = 14;
 //   dL_dscales    -> dL_dlog_scale  = dL_ds * s
 //   dL_drotations -> dL_draw_quat   = (dL_dq - q (q . dL_dq)) / max(|r|, 1e-12)
 template <int C, bool RAW>
-__global__ void __launch_bounds__(PBW_THREADS, 3)
+__global__ void __launch_bounds__(PBW_THREADS, RAW ? 2 : 3)
 preprocess_bwd_kernel(int P, int W, int H, const float* __restrict__ alt_affine, float* __restrict__ alt_sums,
                       const float* __restrict__ means3D, const float* __restrict__ scales,
                       const float4* __restrict__ rotations, const float* __restrict__ cov3D_precomp,
