@@ -123,7 +123,6 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
     const int my_slot = lane < (uint32_t)NV ? (int)lane : -1;
     // The accumulators are kept un-scaled and un-signed; the constant factors of each gradient slot
     // are applied once per flush: mean2D gets -d(pixel)/d(ndc), the conic terms -1/2 (and the opacity, below).
-    const float slot_scale = (my_slot >= 2 && my_slot <= 4) ? -0.5f : 1.f;       // the conic sums carry their -1/2
 
 #if EOGS_COUNT_PAIRS
     unsigned long long cnt_eval = 0ull, cnt_blend = 0ull, cnt_slots = 0ull, cnt_entries = 0ull, cnt_flush = 0ull;   // warp-uniform
@@ -390,8 +389,8 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
 #pragma unroll
                     for (int k = 0; k < NV; k++) v[k] = lo2(v2[k]) + hi2(v2[k]);
                     // The record receives the plain sums: everything that is constant per Gaussian — the opacity on the
-                    // five geometric sums, the conic that turns the two first moments into dL_dmean2D, the pixel -> ndc
-                    // factors — is applied once per Gaussian by preprocess_bwd_kernel (linear, so it commutes with the sum
+                    // five geometric sums, the conic that turns the two first moments into dL_dmean2D, the -1/2 of the conic
+                    // terms, the pixel -> ndc factors — is applied once per Gaussian by preprocess_bwd_kernel (linear, so it commutes with the sum
                     // over tiles) instead of once per (tile, Gaussian) here.
                     __syncwarp();                                    // the previous flush's reads are done
 #pragma unroll
@@ -406,7 +405,7 @@ blend_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ 
                         v[0] = lo2(s) + hi2(s);
                     }
                     v[0] += __shfl_down_sync(FULL, v[0], NV);        // lane k < NV: its half + the half of lane k + NV
-                    if (my_slot >= 0) atomicAdd(grad_rec + (size_t)gid * GRAD_STRIDE + my_slot, v[0] * slot_scale);
+                    if (my_slot >= 0) atomicAdd(grad_rec + (size_t)gid * GRAD_STRIDE + my_slot, v[0]);
                 }
             }
             __syncwarp();

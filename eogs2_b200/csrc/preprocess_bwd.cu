@@ -69,9 +69,9 @@ preprocess_bwd_kernel(int P, int W, int H, const float* __restrict__ alt_affine,
             const float4 gb = __ldg(grad_rec + (size_t)idx * (GRAD_STRIDE / 4) + 1);
             const float4 gc = __ldg(grad_rec + (size_t)idx * (GRAD_STRIDE / 4) + 2);
             // The blend backward accumulated plain sums over the Gaussian's pixels (u = G dL/dalpha):
-            //   ga.x, ga.y = sum u dx, sum u dy;   ga.z, ga.w, gb.x = -1/2 sum u (dx dx, dx dy, dy dy);   gb.y = sum u
+            //   ga.x, ga.y = sum u dx, sum u dy;   ga.z, ga.w, gb.x = sum u (dx dx, dx dy, dy dy);   gb.y = sum u
             // The per-Gaussian constants are applied below, once the conic and the opacity are recomputed:
-            //   dL_dconic = opacity * (ga.z, ga.w, gb.x)                                     (backward.cu:634-640)
+            //   dL_dconic = -1/2 opacity * (ga.z, ga.w, gb.x)                                (backward.cu:634-640)
             //   dL_dmean2D = -(W/2, H/2) * opacity * conic . (sum u dx, sum u dy)            (backward.cu:631-632)
             const float mom_x = ga.x, mom_y = ga.y;
             float dcon_x = ga.z, dcon_y = ga.w, dcon_w = gb.x;
@@ -145,7 +145,8 @@ preprocess_bwd_kernel(int P, int W, int H, const float* __restrict__ alt_affine,
                 const float con_x = c_yy * det_inv, con_y = -c_xy * det_inv, con_z = c_xx * det_inv;
                 g_mean2D[0] = -0.5f * (float)W * op_fwd * (con_x * mom_x + con_y * mom_y);
                 g_mean2D[1] = -0.5f * (float)H * op_fwd * (con_z * mom_y + con_y * mom_x);
-                dcon_x *= op_fwd; dcon_y *= op_fwd; dcon_w *= op_fwd;
+                const float hop = -0.5f * op_fwd;
+                dcon_x *= hop; dcon_y *= hop; dcon_w *= hop;
             }
             const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
             if (denom2inv != 0.f) {
