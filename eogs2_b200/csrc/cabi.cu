@@ -53,6 +53,15 @@ void prof_mark(cudaStream_t s, int stage) {
     cudaEventRecord(p.ev[stage], s);
 }
 
+// The geometry stage's words, stored by the device into the host's mapped pinned struct: payload, system fence, `ready`.
+__global__ void publish_info_kernel(eogs_forward_info* info, volatile eogs_forward_info* host) {
+    host->num_instances = info->num_instances;
+    host->error = info->error;
+    __threadfence_system();
+    host->ready = 1u;
+    info->ready = 1u;
+}
+
 __global__ void fill_u8_kernel(uint8_t* p, int n, uint8_t v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -191,19 +200,26 @@ static int forward_geometry_impl(eogs_stream_t stream, int P, int W, int H, int 
     // its scan, rasterizer_impl.cu:284).  Small scenes: the kernel's last warp writes the pinned struct itself (when it
     // is mapped into the device address space, which cudaHostAlloc / torch pin_memory memory is), see preprocess.cu.
     constexpr int DIRECT_PUBLISH_MAX_P = 1 << 18;
-    eogs_forward_info* host_mapped = (P > 0 && P <= DIRECT_PUBLISH_MAX_P) ? mapped_alias(info_host) : nullptr;
+    eogs_forward_info* host_mapped = P > 0 ? mapped_alias(info_host) : nullptr;
+    const bool in_kernel = host_mapped && P <= DIRECT_PUBLISH_MAX_P;
     if (P > 0) {
         const GeomLayout L = geom_layout(P);
         char* g = static_cast<char*>(geom);
         if (int rc = launch_preprocess_fwd(s, P, W, H, band, channels, raw_params, means3D, scales, rotations,
                                            cov3D_precomp, opacities, colors, viewmatrix, alt_affine, scale_modifier,
-                                           antialiasing != 0, radii, g, L, info_dev, host_mapped)) return rc;
+                                           antialiasing != 0, radii, g, L, info_dev, in_kernel ? host_mapped : nullptr)) return rc;
         prof_mark(s, ST_PREPROCESS);
     }
-    if (!host_mapped) {
-        // Two stream-ordered copies: the payload (I, error) first, the `ready` word second.  A host that sees `ready` set
-        // therefore reads a complete payload (one 16-byte copy gives no such guarantee: CUDA does not promise that a host
-        // thread observes a device -> host copy atomically or in word order before the stream operation completes).
+    if (host_mapped && !in_kernel) {
+        // large scenes: one single-thread kernel behind the projection stores the words into the mapped host struct
+        // (one launch instead of a memset and two copy operations in front of the depth sort)
+        publish_info_kernel<<<1, 1, 0, s>>>(info_dev, host_mapped);
+        EOGS_LAUNCH_CHECK("publish_info_kernel");
+    } else if (!host_mapped) {
+        // Host struct not mapped into the device address space (or P = 0): two stream-ordered copies, the payload (I, error)
+        // first, the `ready` word second.  A host that sees `ready` set therefore reads a complete payload (one 16-byte copy
+        // gives no such guarantee: CUDA does not promise that a host thread observes a device -> host copy atomically or in
+        // word order before the stream operation completes).
         EOGS_CUDA(cudaMemsetAsync(&info_dev->ready, 0x01, sizeof(uint32_t), s));
         if (info_host) {
             EOGS_CUDA(cudaMemcpyAsync(info_host, info_dev, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

@@ -63,9 +63,10 @@ extern "C" {
 typedef void* eogs_stream_t;    /* cudaStream_t */
 
 /* Host-visible result of the geometry stage.  info_host must be pinned host memory.  Its words are written right after
- * the projection kernel, BEFORE the depth sort — by two stream-ordered copies (payload, then `ready`), or, for scenes of
- * up to 2^18 Gaussians whose info_host is mapped into the device address space (cudaHostAlloc / cudaMallocHost / torch
- * pin_memory under unified addressing), by the kernel's last warp itself (payload, system-scope fence, `ready`): a host
+ * the projection kernel, BEFORE the depth sort — by the device itself when info_host is mapped into the device address
+ * space (cudaHostAlloc / cudaMallocHost / torch pin_memory under unified addressing: payload, system-scope fence,
+ * `ready`; by the projection kernel's last warp up to 2^18 Gaussians, by a one-thread kernel behind it above), otherwise
+ * by two stream-ordered copies (payload, then `ready`): a host
  * that zeroes info_host->ready before the call and polls it afterwards has I while the rest of the geometry stage still
  * runs; a host that synchronises the stream sees the same values. */
 typedef struct eogs_forward_info {
