@@ -28,6 +28,12 @@ constexpr int PATCH_W = 8, PATCH_H = 4;
 // same for the left edge.  One sqrt per line (3 lines for 2 bands, bands widened by half a pixel
 // so neighbours share a line) gives all 4 answers exactly.  Margin 0.1 on q (0.05 on the exponent) covers rounding and
 // the approximate sqrt / divide; NaNs compare false and keep the entry.
+__device__ __forceinline__ float fast_sqrt(float x) {     // MUFU.SQRT: 2 ulp, inside region_mask's margin (an IEEE sqrt is ~8 instructions)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ uint32_t region_mask(const float4& r0, const float4& r1, float tx0, float ty0,
                                                 float img_x1, float img_y1) {
     constexpr int ROWS = 2, COLS = 2, RH = 8, RW = 8;
@@ -36,7 +42,7 @@ __device__ __forceinline__ uint32_t region_mask(const float4& r0, const float4& 
     if (qmax <= 0.f) return 0u;
     const float det = A * C - B * B;
     const float inv_det = __fdividef(1.f, det), invA = __fdividef(1.f, A);
-    const float hx = __fsqrt_rn(qmax * C * inv_det), hy = __fsqrt_rn(qmax * A * inv_det);
+    const float hx = fast_sqrt(qmax * C * inv_det), hy = fast_sqrt(qmax * A * inv_det);
     if (mx + hx < tx0 || mx - hx > tx0 + (TILE - 1) || my + hy < ty0 || my - hy > ty0 + (TILE - 1)) return 0u;
     const float slope = -B * invA;
     const float dy_right = __fdividef(-B * hx, C), dy_left = -dy_right;
@@ -46,7 +52,7 @@ __device__ __forceinline__ uint32_t region_mask(const float4& r0, const float4& 
     for (int k = 0; k <= ROWS; k++) {
         dyl[k] = (ty0 + (float)(RH * k) - 0.5f) - my;
         const float dyc = fminf(fmaxf(dyl[k], -hy), hy);
-        const float h = __fsqrt_rn(fmaxf(0.f, Aq - det * dyc * dyc)) * invA;
+        const float h = fast_sqrt(fmaxf(0.f, Aq - det * dyc * dyc)) * invA;
         const float c = mx + slope * dyc;
         xr[k] = c + h;
         xl[k] = c - h;
