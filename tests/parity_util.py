@@ -52,7 +52,7 @@ def assert_no_worse_than_rerun(ours, ref, ref_rerun, what, rtol=1e-3, atol_frac=
     n, worst, bad = violations(ours, ref, rtol, atol_frac)
     n0, worst0, _ = violations(ref_rerun, ref, rtol, atol_frac)
     # one rerun pair is a noisy estimate of the reference's own outlier count (0 .. 20 of 10^6 over repeated runs of the
-    # same case, profiles/r3d_fuzz_parity.json): allow 2e-5 of the Gaussians on top.  A wrong formula puts thousands over.
+    # same case, profiles/r4g_fuzz_parity.json): allow 2e-5 of the Gaussians on top.  A wrong formula puts thousands over.
     slack_rows = max(slack_rows, int(np.ceil(2e-5 * _rows(ref).shape[0])))
     # The COUNT of outlier Gaussians is the robust statistic (a handful in 10^6, the ill-conditioned ones on both sides).
     # Their worst excess is heavy-tailed: between two runs of the reference at 1 M Gaussians it ranged 2e-5 .. 1.4e-4 x

@@ -64,8 +64,11 @@ def one(dev, rng, idx):
             continue
         r = T.rel(t.cpu().numpy(), ref)
         worst = max(worst, r)
-        if r >= T.GRAD_RTOL:
-            bad.append(f"{nm}:{r:.2e}")
+        # the reference's own atomics make it differ from ITSELF between two runs (up to 8e-4 on a single huge Gaussian,
+        # profiles/r4g_fuzz_outlier_case.json): a difference is a mismatch only when it is not explained by that noise
+        r0 = T.rel(gr2[nm].cpu().numpy(), ref)
+        if r >= T.GRAD_RTOL and r > 1.5 * r0 + 1e-4:
+            bad.append(f"{nm}:{r:.2e} (reference vs its rerun {r0:.2e})")
         # per Gaussian, per element (tests/parity_util.py), against the reference's deviation from its own rerun
         n, w, _ = violations(t, gr[nm])
         n0, w0, _ = violations(gr2[nm], gr[nm])
