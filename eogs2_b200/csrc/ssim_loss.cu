@@ -2,7 +2,7 @@
 //     L = (1 - lambda) * mean|img - gt| + lambda * (1 - SSIM(img, gt))          (loss/shadow.py:21-29,
 //         utils/loss_utils.py:18-85: 11x11 Gaussian window sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2)
 // The reference evaluates it with five depthwise F.conv2d calls, ~15 elementwise kernels and their
-// autograd.  Here a 16x16-pixel block stages the 26x26 neighbourhood of
+// autograd.  Here a 32x32-pixel block stages the 42x42 neighbourhood of
 // both images in shared memory, runs the separable window (horizontal then vertical, 5 moments at
 // once), forms the SSIM map and reduces both sums to two device scalars; it also stores the three
 // per-pixel partial derivatives of the map (w.r.t. mu1, E[x^2], E[xy]) so that the backward is again a
@@ -10,15 +10,22 @@
 //     dL/dimg = g * [ (1 - lambda)/N * sign(img - gt) - lambda/N * (W*d_mu1 + 2 img W*d_s11 + gt W*d_s12) ]
 // written straight in the rasterizer's planar [C,H,W] layout (it is the dL_dpix the blend backward reads).
 //
-// HBM-bound: forward reads 8 B and writes 12 B per pixel-channel, backward reads 20 B and writes 4 B;
-// ~150 FMA per pixel-channel from shared memory.
+// Bound: shared-memory instruction issue, not HBM (ncu of the first version: MIO throttle the top stall, DRAM 7-11 %).
+// Both passes are therefore REGISTER-TILED: a thread produces 4 adjacent outputs from a sliding window it holds in
+// registers — the horizontal pass reads its 14 + 2 inputs per image as four LDS.128, the vertical pass reads 14
+// values per map for 4 outputs — 21 shared-memory instructions per output pixel instead of 77, and the halo
+// amplification of the staged tile drops from 2.6x (16x16) to 1.7x (32x32).
+// HBM: forward reads 8 B and writes 12 B per pixel-channel, backward reads 20 B and writes 4 B.
 #include "common.cuh"
 
 namespace eogs {
 
-constexpr int SS_T = 16;                 // output tile
+constexpr int SS_T = 32;                 // output tile (square)
 constexpr int SS_R = 5;                  // window radius (window_size 11)
-constexpr int SS_P = SS_T + 2 * SS_R;    // 26: staged neighbourhood
+constexpr int SS_P = SS_T + 2 * SS_R;    // 42: staged neighbourhood
+constexpr int SS_PITCH = 44;             // staged row pitch in floats: 16-byte aligned rows, columns 42..43 are zero
+constexpr int SS_THREADS = 256;
+constexpr int SS_Q = 4;                  // outputs per thread and pass
 constexpr float SS_C1 = 0.01f * 0.01f, SS_C2 = 0.03f * 0.03f;
 
 struct Window { float w[2 * SS_R + 1]; };
@@ -39,65 +46,106 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_red) {
     return t;                            // valid in thread 0
 }
 
-__global__ void __launch_bounds__(SS_T * SS_T)
+// Stage the 42x42 neighbourhood of one plane (zero padding outside the image, conv2d padding=5) into rows of
+// SS_PITCH floats; the two pad columns are zero.
+__device__ __forceinline__ void stage_plane(const float* __restrict__ src, int H, int W, int x0, int y0,
+                                            float (*dst)[SS_PITCH]) {
+    for (int i = threadIdx.x; i < SS_P * SS_PITCH; i += SS_THREADS) {
+        const int ly = i / SS_PITCH, lx = i - ly * SS_PITCH;
+        const int gy = y0 + ly - SS_R, gx = x0 + lx - SS_R;
+        const bool in = lx < SS_P && gy >= 0 && gy < H && gx >= 0 && gx < W;
+        dst[ly][lx] = in ? __ldg(src + (size_t)gy * W + gx) : 0.f;
+    }
+}
+
+// 16 consecutive floats of a staged row, starting at a multiple of 4: four conflict-free LDS.128
+__device__ __forceinline__ void load16(const float* row, float* v) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4 q = *reinterpret_cast<const float4*>(row + 4 * k);
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
+}
+
+__global__ void __launch_bounds__(SS_THREADS)
 photometric_fwd_kernel(int H, int W, Window win, const float* __restrict__ img, const float* __restrict__ gt,
                        float* __restrict__ maps, float* __restrict__ sums)
 {
-    __shared__ float s_a[SS_P][SS_P + 1], s_b[SS_P][SS_P + 1];
-    __shared__ float s_h[5][SS_P][SS_T + 1];
+    __shared__ __align__(16) float s_a[SS_P][SS_PITCH], s_b[SS_P][SS_PITCH];
+    __shared__ __align__(16) float s_h[5][SS_P][SS_T];
     __shared__ float s_red[8];
-    const int c = blockIdx.z, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c = blockIdx.z;
     const int x0 = blockIdx.x * SS_T, y0 = blockIdx.y * SS_T;
     const size_t plane = (size_t)H * W;
-    const float* pa = img + c * plane;
-    const float* pb = gt + c * plane;
-    for (int i = threadIdx.x; i < SS_P * SS_P; i += SS_T * SS_T) {
-        const int ly = i / SS_P, lx = i - ly * SS_P;
-        const int gy = y0 + ly - SS_R, gx = x0 + lx - SS_R;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;          // zero padding (conv2d padding=5)
-        s_a[ly][lx] = in ? __ldg(pa + (size_t)gy * W + gx) : 0.f;
-        s_b[ly][lx] = in ? __ldg(pb + (size_t)gy * W + gx) : 0.f;
-    }
+    stage_plane(img + c * plane, H, W, x0, y0, s_a);
+    stage_plane(gt + c * plane, H, W, x0, y0, s_b);
     __syncthreads();
-    for (int i = threadIdx.x; i < SS_P * SS_T; i += SS_T * SS_T) {       // horizontal pass, 26 rows x 16 columns
-        const int ly = i / SS_T, lx = i - ly * SS_T;
-        float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    // horizontal pass: 42 rows x 8 items of 4 adjacent outputs
+    for (int it = threadIdx.x; it < SS_P * (SS_T / SS_Q); it += SS_THREADS) {
+        const int ly = it / (SS_T / SS_Q), x = (it - ly * (SS_T / SS_Q)) * SS_Q;
+        float a[16], b[16];
+        load16(&s_a[ly][x], a);
+        load16(&s_b[ly][x], b);
+        float m1[SS_Q], m2[SS_Q], s11[SS_Q], s22[SS_Q], s12[SS_Q];
 #pragma unroll
-        for (int k = 0; k <= 2 * SS_R; k++) {
-            const float a = s_a[ly][lx + k], b = s_b[ly][lx + k], w = win.w[k];
-            m1 = fmaf(w, a, m1); m2 = fmaf(w, b, m2);
-            s11 = fmaf(w, a * a, s11); s22 = fmaf(w, b * b, s22); s12 = fmaf(w, a * b, s12);
+        for (int o = 0; o < SS_Q; o++) { m1[o] = m2[o] = s11[o] = s22[o] = s12[o] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < SS_Q + 2 * SS_R; j++) {                      // input j feeds output o with tap k = j - o
+            const float aa = a[j] * a[j], bb = b[j] * b[j], ab = a[j] * b[j];
+#pragma unroll
+            for (int o = 0; o < SS_Q; o++) {
+                const int k = j - o;
+                if (k < 0 || k > 2 * SS_R) continue;
+                const float w = win.w[k];
+                m1[o] = fmaf(w, a[j], m1[o]); m2[o] = fmaf(w, b[j], m2[o]);
+                s11[o] = fmaf(w, aa, s11[o]); s22[o] = fmaf(w, bb, s22[o]); s12[o] = fmaf(w, ab, s12[o]);
+            }
         }
-        s_h[0][ly][lx] = m1; s_h[1][ly][lx] = m2; s_h[2][ly][lx] = s11; s_h[3][ly][lx] = s22; s_h[4][ly][lx] = s12;
+        *reinterpret_cast<float4*>(&s_h[0][ly][x]) = make_float4(m1[0], m1[1], m1[2], m1[3]);
+        *reinterpret_cast<float4*>(&s_h[1][ly][x]) = make_float4(m2[0], m2[1], m2[2], m2[3]);
+        *reinterpret_cast<float4*>(&s_h[2][ly][x]) = make_float4(s11[0], s11[1], s11[2], s11[3]);
+        *reinterpret_cast<float4*>(&s_h[3][ly][x]) = make_float4(s22[0], s22[1], s22[2], s22[3]);
+        *reinterpret_cast<float4*>(&s_h[4][ly][x]) = make_float4(s12[0], s12[1], s12[2], s12[3]);
     }
     __syncthreads();
-    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    // vertical pass: thread = column tx, output rows 4 ty .. 4 ty + 3
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    float r[5][SS_Q];
 #pragma unroll
-    for (int k = 0; k <= 2 * SS_R; k++) {                                // vertical pass
-        const float w = win.w[k];
-        mu1 = fmaf(w, s_h[0][ty + k][tx], mu1); mu2 = fmaf(w, s_h[1][ty + k][tx], mu2);
-        e11 = fmaf(w, s_h[2][ty + k][tx], e11); e22 = fmaf(w, s_h[3][ty + k][tx], e22);
-        e12 = fmaf(w, s_h[4][ty + k][tx], e12);
+    for (int m = 0; m < 5; m++) {
+        float col[SS_Q + 2 * SS_R];
+#pragma unroll
+        for (int j = 0; j < SS_Q + 2 * SS_R; j++) col[j] = s_h[m][SS_Q * ty + j][tx];
+#pragma unroll
+        for (int o = 0; o < SS_Q; o++) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * SS_R; k++) acc = fmaf(win.w[k], col[o + k], acc);
+            r[m][o] = acc;
+        }
     }
-    const int gx = x0 + tx, gy = y0 + ty;
-    const bool inside = gx < W && gy < H;
+    const int gx = x0 + tx;
     float ssim_v = 0.f, l1_v = 0.f;
-    if (inside) {
+#pragma unroll
+    for (int o = 0; o < SS_Q; o++) {
+        const int gy = y0 + SS_Q * ty + o;
+        if (gx >= W || gy >= H) continue;
+        const float mu1 = r[0][o], mu2 = r[1][o], e11 = r[2][o], e22 = r[3][o], e12 = r[4][o];
         const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
         const float sig1 = e11 - mu1_sq, sig2 = e22 - mu2_sq, sig12 = e12 - mu12;
         const float A = mu1_sq + mu2_sq + SS_C1, B = sig1 + sig2 + SS_C2;
         const float Cn = 2.f * mu12 + SS_C1, D = 2.f * sig12 + SS_C2;
         const float inv_AB = 1.f / (A * B);
-        const float m = Cn * D * inv_AB;
-        ssim_v = m;
+        const float mval = Cn * D * inv_AB;
+        ssim_v += mval;
         // partial derivatives of the map w.r.t. (mu1, E[x^2], E[xy]) at this pixel (mu2, E[y^2] fixed)
-        const float d_mu1 = 2.f * mu2 * (D - Cn) * inv_AB - m * 2.f * mu1 * (B - A) * inv_AB;
-        const float d_s11 = -m / B;
+        const float d_mu1 = 2.f * mu2 * (D - Cn) * inv_AB - mval * 2.f * mu1 * (B - A) * inv_AB;
+        const float d_s11 = -mval / B;
         const float d_s12 = 2.f * Cn * inv_AB;
-        const size_t o = c * plane + (size_t)gy * W + gx;
+        const size_t ofs = c * plane + (size_t)gy * W + gx;
         const size_t stride = (size_t)gridDim.z * plane;
-        maps[o] = d_mu1; maps[stride + o] = d_s11; maps[2 * stride + o] = d_s12;
-        l1_v = fabsf(s_a[ty + SS_R][tx + SS_R] - s_b[ty + SS_R][tx + SS_R]);
+        maps[ofs] = d_mu1; maps[stride + ofs] = d_s11; maps[2 * stride + ofs] = d_s12;
+        l1_v += fabsf(s_a[SS_Q * ty + o + SS_R][tx + SS_R] - s_b[SS_Q * ty + o + SS_R][tx + SS_R]);
     }
     const float bs = block_sum_256(ssim_v, s_red);
     const float bl = block_sum_256(l1_v, s_red);
@@ -111,51 +159,65 @@ __global__ void photometric_finish_kernel(float inv_n, float lambda, const float
     out[2] = l1_mean;
 }
 
-__global__ void __launch_bounds__(SS_T * SS_T)
+__global__ void __launch_bounds__(SS_THREADS)
 photometric_bwd_kernel(int H, int W, Window win, float inv_n, float lambda, const float* __restrict__ img,
                        const float* __restrict__ gt, const float* __restrict__ maps,
                        const float* __restrict__ dL_dloss, float* __restrict__ dL_dimg)
 {
-    __shared__ float s_m[3][SS_P][SS_P + 1];
-    __shared__ float s_h[3][SS_P][SS_T + 1];
-    const int c = blockIdx.z, tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    __shared__ __align__(16) float s_m[3][SS_P][SS_PITCH];
+    __shared__ __align__(16) float s_h[3][SS_P][SS_T];
+    const int c = blockIdx.z;
     const int x0 = blockIdx.x * SS_T, y0 = blockIdx.y * SS_T;
     const size_t plane = (size_t)H * W, stride = (size_t)gridDim.z * plane;
-    for (int i = threadIdx.x; i < SS_P * SS_P; i += SS_T * SS_T) {
-        const int ly = i / SS_P, lx = i - ly * SS_P;
-        const int gy = y0 + ly - SS_R, gx = x0 + lx - SS_R;
-        const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
-        const size_t o = c * plane + (size_t)gy * W + gx;
 #pragma unroll
-        for (int k = 0; k < 3; k++) s_m[k][ly][lx] = in ? __ldg(maps + k * stride + o) : 0.f;
-    }
+    for (int k = 0; k < 3; k++) stage_plane(maps + k * stride + c * plane, H, W, x0, y0, s_m[k]);
     __syncthreads();
-    for (int i = threadIdx.x; i < SS_P * SS_T; i += SS_T * SS_T) {
-        const int ly = i / SS_T, lx = i - ly * SS_T;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int it = threadIdx.x; it < SS_P * (SS_T / SS_Q); it += SS_THREADS) {
+        const int ly = it / (SS_T / SS_Q), x = (it - ly * (SS_T / SS_Q)) * SS_Q;
 #pragma unroll
-        for (int k = 0; k <= 2 * SS_R; k++) {
-            const float w = win.w[k];
-            a0 = fmaf(w, s_m[0][ly][lx + k], a0); a1 = fmaf(w, s_m[1][ly][lx + k], a1); a2 = fmaf(w, s_m[2][ly][lx + k], a2);
+        for (int m = 0; m < 3; m++) {
+            float v[16], acc[SS_Q] = {0.f, 0.f, 0.f, 0.f};
+            load16(&s_m[m][ly][x], v);
+#pragma unroll
+            for (int j = 0; j < SS_Q + 2 * SS_R; j++)
+#pragma unroll
+                for (int o = 0; o < SS_Q; o++) {
+                    const int k = j - o;
+                    if (k < 0 || k > 2 * SS_R) continue;
+                    acc[o] = fmaf(win.w[k], v[j], acc[o]);
+                }
+            *reinterpret_cast<float4*>(&s_h[m][ly][x]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         }
-        s_h[0][ly][lx] = a0; s_h[1][ly][lx] = a1; s_h[2][ly][lx] = a2;
     }
     __syncthreads();
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= W || gy >= H) return;
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    float r[3][SS_Q];
 #pragma unroll
-    for (int k = 0; k <= 2 * SS_R; k++) {
-        const float w = win.w[k];
-        c0 = fmaf(w, s_h[0][ty + k][tx], c0); c1 = fmaf(w, s_h[1][ty + k][tx], c1); c2 = fmaf(w, s_h[2][ty + k][tx], c2);
+    for (int m = 0; m < 3; m++) {
+        float col[SS_Q + 2 * SS_R];
+#pragma unroll
+        for (int j = 0; j < SS_Q + 2 * SS_R; j++) col[j] = s_h[m][SS_Q * ty + j][tx];
+#pragma unroll
+        for (int o = 0; o < SS_Q; o++) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k <= 2 * SS_R; k++) acc = fmaf(win.w[k], col[o + k], acc);
+            r[m][o] = acc;
+        }
     }
-    const size_t o = c * plane + (size_t)gy * W + gx;
-    const float a = __ldg(img + o), b = __ldg(gt + o);
-    const float d_ssim = c0 + 2.f * a * c1 + b * c2;
-    const float diff = a - b;
-    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);       // torch.abs backward: sign(0) = 0
+    const int gx = x0 + tx;
     const float g = dL_dloss ? __ldg(dL_dloss) : 1.f;
-    dL_dimg[o] = g * inv_n * ((1.f - lambda) * sgn - lambda * d_ssim);
+#pragma unroll
+    for (int o = 0; o < SS_Q; o++) {
+        const int gy = y0 + SS_Q * ty + o;
+        if (gx >= W || gy >= H) continue;
+        const size_t ofs = c * plane + (size_t)gy * W + gx;
+        const float a = __ldg(img + ofs), b = __ldg(gt + ofs);
+        const float d_ssim = r[0][o] + 2.f * a * r[1][o] + b * r[2][o];
+        const float diff = a - b;
+        const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);   // torch.abs backward: sign(0) = 0
+        dL_dimg[ofs] = g * inv_n * ((1.f - lambda) * sgn - lambda * d_ssim);
+    }
 }
 
 }  // namespace eogs
@@ -175,7 +237,7 @@ EOGS_API int eogs_photometric_forward(eogs_stream_t stream, int C, int H, int W,
     for (int k = 0; k < 2 * SS_R + 1; k++) win.w[k] = window11[k];      // host array
     EOGS_CUDA(cudaMemsetAsync(sums2, 0, 2 * sizeof(float), s));
     const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, C);
-    photometric_fwd_kernel<<<grid, SS_T * SS_T, 0, s>>>(H, W, win, image, gt, maps, sums2);
+    photometric_fwd_kernel<<<grid, SS_THREADS, 0, s>>>(H, W, win, image, gt, maps, sums2);
     EOGS_LAUNCH_CHECK("photometric_fwd_kernel");
     photometric_finish_kernel<<<1, 1, 0, s>>>(1.f / ((float)C * (float)H * (float)W), lambda_dssim, sums2, out3);
     EOGS_LAUNCH_CHECK("photometric_finish_kernel");
@@ -191,7 +253,7 @@ EOGS_API int eogs_photometric_backward(eogs_stream_t stream, int C, int H, int W
     Window win;
     for (int k = 0; k < 2 * SS_R + 1; k++) win.w[k] = window11[k];
     const dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T, C);
-    photometric_bwd_kernel<<<grid, SS_T * SS_T, 0, static_cast<cudaStream_t>(stream)>>>(
+    photometric_bwd_kernel<<<grid, SS_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
         H, W, win, 1.f / ((float)C * (float)H * (float)W), lambda_dssim, image, gt, maps, dL_dloss, dL_dimage);
     EOGS_LAUNCH_CHECK("photometric_bwd_kernel");
     return 0;
