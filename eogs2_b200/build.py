@@ -88,12 +88,18 @@ def build_count(force: bool = False) -> Path:
     return build(force, False, COUNT_LIB, PKG_DIR / "csrc" / "build_count", ["-DEOGS_COUNT_PAIRS=1"])
 
 
+# the rasterizer path: what a profile of the render / backward kernels depends on (the loss, resample, optimiser, knn and
+# DSM kernels live in their own files and do not change it)
+RASTER_SOURCES = ["cabi.cu", "preprocess.cu", "binning.cu", "blend_fwd.cu", "blend_bwd.cu", "preprocess_bwd.cu",
+                  "common.cuh", "blend_common.cuh", "f32x2.cuh", "geom_math.cuh"]
+
+
 def source_hash() -> str:
-    """sha256 over the CUDA sources and the public header: ties a committed ncu capture (profiles/ncu_current.json) to
-    the kernels it was taken from."""
+    """sha256 over the CUDA sources of the rasterizer path and the public header: ties a committed ncu capture
+    (profiles/ncu_current.json) to the kernels it was taken from."""
     import hashlib
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "eogs_raster.h"]):
+    for p in sorted([CSRC / n for n in RASTER_SOURCES] + [PKG_DIR.parent / "include" / "eogs_raster.h"]):
         h.update(p.name.encode()); h.update(p.read_bytes())
     return h.hexdigest()
 
