@@ -22,9 +22,10 @@
 //   replay    per surviving entry and per set region bit: recompute G and alpha with the
 //             forward's exact expression, vote, and for accepted pixels update T, the running
 //             "colour behind" dot product and the 11 accumulators.  Per-pixel constants
-//             (dL_dpixel, T_final * bg.dL_dpixel) live in shared memory, lane-contiguous
-//             (conflict-free LDS.128), the dynamic state (T, accum, n_contrib) in registers.
-//   flush     the 6+C per-lane partial sums cross the warp through shared memory: 11 conflict-free STS
+//             (dL_dpixel, T_final * bg.dL_dpixel, n_contrib) live in shared memory, lane-contiguous
+//             (conflict-free LDS.128), the dynamic state (T, accum) in registers.
+//   flush     the 6+C per-lane partial sums (plain sums: every per-Gaussian constant factor is applied later, once per
+//             Gaussian, by preprocess_bwd_kernel) cross the warp through shared memory: 11 conflict-free STS
 //             ([value][lane]), then lane (k, h) adds half a row (4 x LDS.128, packed adds), one shuffle
 //             joins the halves and lanes 0..10 issue ONE red.global.add.f32 warp instruction into the
 //             Gaussian's 64-byte record.  (The transposing shuffle butterfly it replaces — 13 SHFL + 22

@@ -1,11 +1,10 @@
-// Pieces shared by the forward and backward blend kernels: the exact culling test, the warp
-// reduction of the backward's per-Gaussian terms, and the approximate MUFU wrappers.
+// Pieces shared by the forward and backward blend kernels: the exact culling test and the approximate MUFU wrappers.
 //
-// A 16x16 tile is cut into four 8x8 pixel REGIONS (and, for the backward's pixel ownership, eight 8x4 patches:
-// patch p: x in [8*(p&1), +7], y in [4*(p>>1), +3]).  The forward thread that stages a list entry decides ONCE
-// which regions the Gaussian can reach with alpha >= 1/255 (region_mask below): the forward kernel (128 threads,
-// warp = one region) appends the entry only to the regions it reaches and stores the mask, one byte per instance;
-// the backward kernel (one warp per tile) reads it, never fetches entries nobody reaches and skips half tiles.
+// A 16x16 tile is cut into four 8x8 pixel REGIONS (bit q of a mask = region (8*(q&1), 8*(q>>1))).  The forward thread
+// that stages a list entry decides ONCE which regions the Gaussian can reach with alpha >= 1/255 (region_mask below):
+// the forward kernel (128 threads, warp = one region) appends the entry only to the regions it reaches and stores the
+// mask, one byte per instance; the backward kernel (one warp per tile, the same pixel-to-lane map) reads it, never
+// fetches entries nobody reaches and evaluates only the regions of the mask.
 // The reference evaluates every entry of the tile list in every one of the 256 threads (forward.cu:356-372,
 // backward.cu:551-577).
 // Culling is exact and conservative: it only removes (pixel, Gaussian) pairs that the per-pixel test
