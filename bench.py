@@ -646,8 +646,8 @@ def main():
         # write straight into views of it (no packing copies); it is all-reduced over NVLink inside the step.
         P = P_GAUSS
         from eogs2_b200.nvls import make_grad_exchange
-        # the exchange is the library's own NVLS kernel (multimem.ld_reduce + multimem.st on a symmetric-memory bucket)
-        # or ncclAllReduce, whichever a short calibration finds faster on this box; named in config["allreduce"]
+        # the exchange is the library's own NVLS kernel (multimem.ld_reduce + multimem.st on a symmetric-memory bucket),
+        # its peer-to-peer kernel (2-4 GPUs) or ncclAllReduce, whichever a short calibration finds faster on this box; named in config["allreduce"]
         bucket, exchange, exchange_name = make_grad_exchange(16 * P + 16, dev)
         views = {"means3D": bucket[0:3 * P].view(P, 3), "colors": bucket[3 * P:8 * P].view(P, 5),
                  "opacity": bucket[8 * P:9 * P].view(P, 1), "scales": bucket[9 * P:12 * P].view(P, 3),
@@ -713,7 +713,7 @@ def main():
         # (2) the exchange alone, and a bit check of the own kernel against ncclAllReduce on the same data
         ex_ms, _ = timed_steps(lambda: None, args.steps, args.warmup, lambda: None, world, post)
         check = None
-        if exchange_name.startswith("own NVLS"):
+        if exchange_name.startswith("own "):
             gen = torch.Generator(device=dev).manual_seed(1234 + rank)
             pattern = torch.randn(bucket.numel(), device=dev, generator=gen)
             bucket.copy_(pattern); exchange(); mine = bucket.clone()
@@ -754,9 +754,9 @@ def main():
         line["config5"] = c5
     if rank == 0:
         # preprocess, 4 binning passes (count / scan / offsets / scatter) x rows and columns, blend fwd, tile order,
-        # blend bwd, preprocess bwd (+ the NVLS all-reduce kernel when it is the chosen exchange); the CUB depth sort
+        # blend bwd, preprocess bwd (+ the own all-reduce kernel when it is the chosen exchange); the CUB depth sort
         # and torch's fill / barrier kernels are not counted
-        own = 1 + 8 + 2 + 2 + (1 if world > 1 and exchange_name.startswith("own NVLS") else 0)
+        own = 1 + 8 + 2 + 2 + (1 if world > 1 and exchange_name.startswith("own ") else 0)
         line["gpu_launches"] = own * args.steps
         line["roofline"] = roofline_report(stage_ms, I, peaks, hbm_peak, peak_src, clocks)
         if world == 1 and not args.no_cpu_baseline:

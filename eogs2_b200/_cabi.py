@@ -97,6 +97,7 @@ SIGNATURES = {
     "eogs_dsm_splat": (C.c_int, [c_ptr, C.c_longlong, c_ptr, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                  C.c_int, C.c_float, c_ptr, c_f32p]),
     "eogs_nvls_allreduce": (C.c_int, [c_ptr, c_ptr, C.c_ulonglong, C.c_int, C.c_int]),
+    "eogs_p2p_allreduce": (C.c_int, [c_ptr, c_ptr, C.c_ulonglong, C.c_int, C.c_int]),
     "eogs_mark_visible": (C.c_int, [c_ptr, C.c_int, c_f32p, c_f32p, c_f32p, c_ptr]),
     "eogs_profile_enable": (C.c_int, [C.c_int]),
     "eogs_profile_read": (C.c_int, [c_ptr, C.c_int]),

@@ -25,6 +25,9 @@ class SymmetricBucket:
         self.flat, self.handle, self.group = flat, handle, group
         self.rank, self.world = int(handle.rank), int(handle.world_size)
         self._phase = 0
+        # every rank's copy of the bucket as mapped into this process (peer-to-peer variant of the collective)
+        ptrs = [int(p) for p in getattr(handle, "buffer_ptrs", [])]
+        self._peer_ptrs = (C.c_void_p * self.world)(*ptrs) if len(ptrs) == self.world and self.world <= 8 and all(ptrs) else None
 
     @classmethod
     def create(cls, numel: int, device: torch.device, group=None) -> Optional["SymmetricBucket"]:
@@ -65,6 +68,26 @@ class SymmetricBucket:
             self._phase ^= 2
         return self.flat
 
+    @property
+    def has_p2p(self) -> bool:
+        return self._peer_ptrs is not None
+
+    def all_reduce_p2p(self) -> torch.Tensor:
+        """Same contract through the peer-to-peer kernel (csrc/nvls.cu: p2p_allreduce_kernel): this rank sums its slice out
+        of every rank's copy over NVLink and stores it into every copy — the faster one on 2 GPUs."""
+        if self._peer_ptrs is None:
+            raise _cabi.EogsRasterError("peer buffer pointers are not available: use all_reduce() or NCCL")
+        lib = _cabi.load()
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self.handle.barrier(channel=self._phase, timeout_ms=20000)
+            _cabi.check(lib.eogs_p2p_allreduce(C.c_void_p(stream), self._peer_ptrs, C.c_ulonglong(self.flat.numel()),
+                                               self.rank, self.world), "eogs_p2p_allreduce")
+            self.handle.barrier(channel=self._phase + 1, timeout_ms=20000)
+            self._phase ^= 2
+        return self.flat
+
 
 def make_grad_exchange(numel: int, device: torch.device, group=None, calibrate: bool = True):
     """The data-parallel step's gradient exchange: returns (flat_bucket, all_reduce, name).
@@ -99,13 +122,19 @@ def make_grad_exchange(numel: int, device: torch.device, group=None, calibrate: 
             e1.record()
             torch.cuda.synchronize(device)
             return e0.elapsed_time(e1) / reps
-        t = torch.tensor([timed(sym.all_reduce), timed(nccl)], dtype=torch.float64, device=device)
+        use_p2p = sym.has_p2p and sym.world <= 4                          # (larger worlds: the switch's reduction wins)
+        t = torch.tensor([timed(sym.all_reduce), timed(nccl), timed(sym.all_reduce_p2p) if use_p2p else 1e9],
+                         dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)            # same decision on every rank
-        choice = "nvls" if float(t[0]) <= float(t[1]) else "nccl"
+        best = int(torch.argmin(t).item())
+        choice = ("nvls", "nccl", "p2p")[best]
         flat.zero_()
-        timing = f" (calibration: own kernel {float(t[0]):.3f} ms, NCCL {float(t[1]):.3f} ms)"
+        timing = f" (calibration: own NVLS kernel {float(t[0]):.3f} ms, NCCL {float(t[1]):.3f} ms" + \
+                 (f", own peer-to-peer kernel {float(t[2]):.3f} ms)" if use_p2p else ")")
     else:
         timing = ""
+    if choice == "p2p":
+        return flat, sym.all_reduce_p2p, "own peer-to-peer kernel: NVLink loads + stores over symmetric memory" + timing
     if choice == "nvls":
         return flat, sym.all_reduce, "own NVLS kernel: multimem.ld_reduce + multimem.st over symmetric memory" + timing
     return flat, nccl, "ncclAllReduce" + timing

@@ -352,6 +352,11 @@ EOGS_API int eogs_dsm_splat(eogs_stream_t stream, long long N, const double* clo
  * brackets the call with cross-GPU barriers (before: all ranks' gradients written; after: all slices landed).
  *   multicast_ptr: the multicast mapping of the bucket (NULL -> error: fall back to NCCL); n_floats % 4 == 0 */
 EOGS_API int eogs_nvls_allreduce(eogs_stream_t stream, void* multicast_ptr, unsigned long long n_floats, int rank, int world);
+/* Peer-to-peer variant for small worlds (2 GPUs: nothing to gain from the switch's reduction): this rank sums its 1/world
+ * slice out of every rank's copy with plain NVLink loads and stores the result into every copy.  buffer_ptrs: HOST array
+ * of `world` device pointers, entry r = rank r's copy of the bucket as mapped into this process (symmetric memory).
+ * Same barrier contract as eogs_nvls_allreduce. */
+EOGS_API int eogs_p2p_allreduce(eogs_stream_t stream, void* const* buffer_ptrs, unsigned long long n_floats, int rank, int world);
 
 /* ---- markVisible ------------------------------------------------------------------- */
 /* The reference's in_frustum culls nothing for affine cameras (its body is

@@ -26,6 +26,7 @@ def test_nvls_allreduce_matches_nccl_on_two_ranks():
     if not out["nvls"]:
         pytest.skip("NVLS multicast not available on this box")
     assert out["max_rel_err_vs_nccl"] <= 1e-6
+    assert out["p2p"] and out["p2p_max_rel_err_vs_nccl"] <= 1e-6        # the peer-to-peer kernel (the 2-GPU exchange)
     assert out["grad_bucket_auto"]["ok"]
 
 

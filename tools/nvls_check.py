@@ -35,6 +35,21 @@ if bucket is not None:
         dist.broadcast(same, 0)
         assert torch.equal(same, bucket.flat), "ranks disagree on the reduced bucket"
     out["max_rel_err_vs_nccl"] = max(errs)
+    out["p2p"] = bucket.has_p2p
+    if bucket.has_p2p:                                # the peer-to-peer kernel: same checks
+        errs = []
+        for trial in range(3):
+            x = torch.randn(n, device=dev, generator=g)
+            ref = x.clone()
+            dist.all_reduce(ref)
+            bucket.flat.copy_(x)
+            bucket.all_reduce_p2p()
+            torch.cuda.synchronize()
+            errs.append(float((bucket.flat - ref).abs().max() / ref.abs().max()))
+            same = bucket.flat.clone()
+            dist.broadcast(same, 0)
+            assert torch.equal(same, bucket.flat), "ranks disagree on the reduced bucket (p2p)"
+        out["p2p_max_rel_err_vs_nccl"] = max(errs)
 
     def timeit(fn, reps=30):
         for _ in range(5):
@@ -51,6 +66,8 @@ if bucket is not None:
     y = torch.randn(n, device=dev)
     out["nccl_ms"] = timeit(lambda: dist.all_reduce(y))
     out["nvls_ms"] = timeit(bucket.all_reduce)
+    if bucket.has_p2p:
+        out["p2p_ms"] = timeit(bucket.all_reduce_p2p)
     import ctypes as C
     from eogs2_b200 import _cabi
     lib = _cabi.load()
