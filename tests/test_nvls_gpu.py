@@ -36,3 +36,23 @@ def test_no_multicast_pointer_is_an_error_not_a_fallback(cuda_dev):
     lib = _cabi.load()
     rc = lib.eogs_nvls_allreduce(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(None), 1024, 0, 2)
     assert rc != 0 and b"NCCL" in lib.eogs_last_error()
+
+
+def test_p2p_allreduce_rejects_bad_arguments(cuda_dev):
+    """The peer-to-peer variant: no buffer table, a null peer, a misaligned peer or an impossible world are errors
+    (never a silent fallback); world = 1 with the rank's own buffer is the identity."""
+    import ctypes as C
+    from eogs2_b200 import _cabi
+    lib = _cabi.load()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x = torch.arange(1024, dtype=torch.float32, device=cuda_dev)
+    assert lib.eogs_p2p_allreduce(stream, C.c_void_p(None), 1024, 0, 2) != 0
+    two = (C.c_void_p * 2)(x.data_ptr(), None)
+    assert lib.eogs_p2p_allreduce(stream, two, 1024, 0, 2) != 0 and b"peer buffer 1" in lib.eogs_last_error()
+    mis = (C.c_void_p * 2)(x.data_ptr(), x.data_ptr() + 4)
+    assert lib.eogs_p2p_allreduce(stream, mis, 1020, 0, 2) != 0
+    assert lib.eogs_p2p_allreduce(stream, two, 1024, 0, 9) != 0
+    one = (C.c_void_p * 1)(x.data_ptr())
+    assert lib.eogs_p2p_allreduce(stream, one, 1024, 0, 1) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(x, torch.arange(1024, dtype=torch.float32, device=cuda_dev))
